@@ -149,3 +149,66 @@ def snapshot_from_lists(number, redshift, halo_ids, part_lists, type_lists=None,
     return Snapshot(number=number, redshift=redshift, halo_id=np.asarray(halo_ids, np.uint64),
                     npart=np.asarray(npart if npart is not None else counts, np.int32),
                     offsets=offsets, pid=pid, ptype=pt)
+
+
+# ----------------------------------------------------------------------------------------
+# hand-crafted adversarial cases (SURVEY.md section 8c list)
+
+def _ids(number, n):
+    return [number * 10**12 + i + 1 for i in range(n)]
+
+
+def case_threshold_edges(min_part_cmp=10, min_part_halo=30):
+    """sum nCommon == minPartCmp (rejected) / +1 (kept); nAllPart == minPartHalo (no token) / +1."""
+    base = 1000
+    def rng(a, n):
+        return list(range(base + a, base + a + n))
+    later = [
+        rng(0, 100),                     # A0: shares 10 with B0 (rejected) and 11 with B1 (kept)
+        rng(1000, min_part_halo),        # A1: no progenitor, nAllPart == minPartHalo  -> vanishes
+        rng(2000, min_part_halo + 1),    # A2: no progenitor, nAllPart == minPartHalo+1 -> token (if tracking on)
+        rng(3000, 200),                  # A3: plain 1:1 match
+    ]
+    earlier = [
+        rng(0, min_part_cmp) + rng(50000, 40),
+        rng(min_part_cmp, min_part_cmp + 1) + rng(51000, 40),
+        rng(3000, 180) + rng(52000, 10),
+        rng(60000, 25),                  # B3: unrelated small halo
+    ]
+    return [snapshot_from_lists(20, 0.1, _ids(20, len(earlier)), earlier),
+            snapshot_from_lists(21, 0.0, _ids(21, len(later)), later)]
+
+
+def case_merit_tie():
+    """Two candidates with catalogue npart 0 -> both merits are exactly 0.0f -> SortIndexes
+    duplicates the first and drops the second (reference src/utils.cpp:438-439); a third,
+    ordinary candidate sorts in front.  Also a halo with catalogue npart > 2^24 (float rounding
+    of the size ratio)."""
+    def rng(a, n):
+        return list(range(a, a + n))
+    later = [rng(100, 300), rng(5000, 120), rng(9000, 64)]
+    earlier = [rng(100, 20) + rng(70000, 5), rng(120, 30) + rng(71000, 5), rng(150, 100) + rng(72000, 5),
+               rng(5000, 100), rng(5100, 20) + rng(9000, 60)]
+    npart_e = [0, 0, 105, 16777217, 80]
+    npart_l = [300, 33554435, 64]
+    return [snapshot_from_lists(30, 0.1, _ids(30, 5), earlier, npart=npart_e),
+            snapshot_from_lists(31, 0.0, _ids(31, 3), later, npart=npart_l)]
+
+
+def case_permuted_ids(seed=3):
+    """Same memberships as make_chain(seed) but with hashed (unordered) halo IDs: changes iM."""
+    return make_chain(seed=seed, n_snaps=5, n_halos=70, id_mode="hashed")
+
+
+def case_duplicate_membership():
+    """One pid listed several times in the same halo and in several halos of both catalogues."""
+    later = [[1, 1, 2, 3] + list(range(100, 140)), [2, 3, 3] + list(range(200, 240)), list(range(100, 130))]
+    earlier = [[1, 2, 2, 3] + list(range(100, 135)), [1, 3] + list(range(200, 238)) + list(range(120, 135))]
+    return [snapshot_from_lists(40, 0.1, _ids(40, 2), earlier), snapshot_from_lists(41, 0.0, _ids(41, 3), later)]
+
+
+def case_empty_and_ragged():
+    """A later catalogue whose halos share nothing with the earlier one, plus 1-particle halos."""
+    later = [list(range(10, 60)), [7], list(range(1000, 1100))]
+    earlier = [list(range(5000, 5050)), [7], list(range(2000, 2040))]
+    return [snapshot_from_lists(50, 0.1, _ids(50, 3), earlier), snapshot_from_lists(51, 0.0, _ids(51, 3), later)]
