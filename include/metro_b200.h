@@ -1,0 +1,177 @@
+/* metro_b200.h -- C ABI of the B200 progenitor-matching engine (libmetro_b200.so).
+ *
+ * Drop-in boundary for MetroCPP's matching hot path.  The reference has no FFI:
+ * its de-facto interface is four free functions over process globals
+ * (reference src/MergerTree.h:85-98, src/utils.h:47, callers src/main.cpp:199-301).
+ * Each entry point below names the reference call it replaces.  Plain pointers and
+ * sizes only; every call returns a status code (0 = METRO_OK) and never exits the
+ * process (the reference prints and exit(0)s, src/utils.cpp:74-78).
+ *
+ * Catalogue 0 is the LATER snapshot (descendants), catalogue 1 the EARLIER one
+ * (progenitors), exactly like locHalos[0] / locHalos[1] (src/main.cpp:154-308).
+ * A "tuple" is one line of an AHF _particles file: (particle ID, halo, type).
+ *
+ * Threading: one context per process/GPU; calls on a context are serialised by
+ * the caller (the reference is single-threaded per rank too).
+ * There is NO CPU fallback: every entry point fails with METRO_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef METRO_B200_H
+#define METRO_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define METRO_OK               0
+#define METRO_ERR_INVALID      1   /* bad argument (null pointer, index out of range, nptypes ...) */
+#define METRO_ERR_CUDA         2   /* CUDA runtime failure, see metro_last_error()               */
+#define METRO_ERR_UNSUPPORTED  3   /* e.g. pid bits + halo bits + type bits do not fit 64 bits   */
+#define METRO_ERR_STATE        4   /* call order (match before upload, fetch before match ...)   */
+#define METRO_ERR_COMM         5   /* NCCL failure                                               */
+
+/* Which build of the reference to reproduce for token (orphan) halos:
+ * GATHER = -DGATHER_TREES full-box build, token particle lists copied once
+ *          (src/Communication.cpp:519-524);
+ * ZOOM_DUP = -DZOOM build, lists are push_back()ed and then appended again, so a token's
+ *          tuples double at every orphan step (src/MergerTree.cpp:597-603). */
+#define METRO_FLAVOUR_GATHER   0
+#define METRO_FLAVOUR_ZOOM_DUP 1
+
+typedef struct metro_ctx metro_ctx;
+
+/* Run-time settings of the path == the globals the reference reads
+ * (src/global_vars.h:92-118; parsed by IOSettings::InitFromCfgFile, src/IOSettings.cpp:153-175). */
+typedef struct {
+	int32_t nptypes;            /* NPTYPES (compile-time in the reference), 1..8            */
+	int32_t min_part_cmp;       /* minPartCmp                                               */
+	int32_t min_part_halo;      /* minPartHalo                                              */
+	int32_t fac_orphan_steps;   /* facOrphanSteps, must be != 0                             */
+	int32_t max_orphan_steps;   /* maxOrphanSteps, 0 = unset = orphan tracking off          */
+	int32_t flavour;            /* METRO_FLAVOUR_*                                          */
+} metro_params;
+
+/* One catalogue as the reference holds it after ReadHalos + ReadParticles
+ * (locHalos[i], locMapParts[i]; src/IOSettings.cpp:551-811).  Host pointers. */
+typedef struct {
+	int64_t n_halos;
+	const uint64_t *halo_id;        /* [H]  Halo::ID                                        */
+	const int32_t *npart;           /* [H * nptypes]  Halo::nPart                           */
+	const int32_t *n_orphan_steps;  /* [H]  Halo::nOrphanSteps (may be NULL = all 0)        */
+	const uint8_t *is_token;        /* [H]  Halo::isToken      (may be NULL = all 0)        */
+	int64_t n_tuples;
+	const uint64_t *pid;            /* [N]  particle IDs                                    */
+	const uint32_t *halo;           /* [N]  index of the owning halo in this catalogue      */
+	const uint8_t *type;            /* [N]  particle type < nptypes (NULL = all 1, NOPTYPE) */
+} metro_catalogue;
+
+/* Sizes of the result of the last metro_match_pair(). */
+typedef struct {
+	int64_t n_halos[2];             /* halos of catalogue 0 / 1                              */
+	int64_t raw_count[2];           /* candidates in the forward / backward raw trees        */
+	int64_t n_trees;                /* clean trees (locCleanTrees[iStep-1].size())           */
+	int64_t clean_count;            /* progenitor entries over all clean trees               */
+	int64_t n_tokens;               /* orphan halos that become token halos                  */
+	int64_t n_untracked;            /* orphans dropped ("untracked", src/MergerTree.cpp:614) */
+	int64_t n_hits;                 /* sum over pid of mA*mB                                 */
+	int64_t n_pairs;                /* distinct (A,B) halo pairs with >= 1 shared tuple      */
+	int64_t n_tuples[2];
+	int32_t pid_bits, halo_bits, type_bits, sort_passes;
+} metro_result_info;
+
+/* Host destination arrays for metro_result_fetch(); any pointer may be NULL (skipped).
+ * Layout mirrors the MergerTree fields (src/MergerTree.h:30-51) in CSR form. */
+typedef struct {
+	/* raw trees locMTrees[d]: d = 0 forward (per halo of catalogue 0, entries index catalogue 1),
+	 * d = 1 backward.  Entries are in final SortByMerit order incl. the SortIndexes tie quirk. */
+	int64_t *raw_off[2];            /* [H_d + 1]                                             */
+	int32_t *raw_prog[2];           /* [raw_count[d]]                                        */
+	int32_t *raw_ncommon[2];        /* [raw_count[d] * nptypes]   MergerTree::nCommon        */
+	uint32_t *raw_merit[2];         /* [raw_count[d]] fp32 bits (0 where the tree was not sorted) */
+	/* clean trees locCleanTrees[iStep-1], in catalogue-0 order */
+	int32_t *tree_main;             /* [n_trees] index into catalogue 0 (mainHalo)           */
+	uint8_t *tree_orphan;           /* [n_trees] MergerTree::isOrphan                        */
+	int64_t *tree_off;              /* [n_trees + 1]                                         */
+	int32_t *clean_prog;            /* [clean_count] catalogue-1 index; -1 = token copy of mainHalo */
+	int32_t *clean_ncommon;         /* [clean_count * nptypes]                               */
+	int32_t *token_halo;            /* [n_tokens] catalogue-0 indices, catalogue order       */
+} metro_result_arrays;
+
+/* Device timings (CUDA events on the context's stream) of the last metro_match_pair(), ms. */
+typedef struct {
+	float total, pack_hist, sort, join, select;
+	int32_t sort_launches, total_launches;
+	float sort_pass_ms[8];
+} metro_timings;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* Replaces InitLocVariables + InitTrees (src/utils.cpp:43-67, src/MergerTree.cpp:503-506). */
+int metro_ctx_create(int device, metro_ctx **out);
+void metro_ctx_destroy(metro_ctx *ctx);
+const char *metro_last_error(const metro_ctx *ctx);   /* ctx may be NULL: last create error */
+const char *metro_version(void);
+
+/* ---- catalogues ---------------------------------------------------------------------- */
+/* Replaces the map build of IOSettings::ReadParticles (locMapParts[slot][pid].push_back,
+ * src/IOSettings.cpp:628-632) and the locHalos[slot] fill (:775-793): copies the host arrays
+ * to HBM.  slot in {0,1}.  Caller keeps ownership of the host arrays. */
+int metro_catalogue_upload(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat);
+/* Same, but the tuple arrays are already DEVICE pointers (zero copy; the context borrows them
+ * until the next upload/shift of that slot).  Halo arrays stay host pointers. */
+int metro_catalogue_adopt_device(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* Replaces FindProgenitors(0,1); FindProgenitors(1,0); CleanTrees(iStep)
+ * (src/MergerTree.cpp:399-499, 133-244, 510-652; called from src/main.cpp:199,217,254|280). */
+int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info *info);
+/* Copies the result of the last match to host arrays (what WriteTree consumes,
+ * src/IOSettings.cpp:1074-1138). */
+int metro_result_fetch(metro_ctx *ctx, const metro_result_arrays *dst);
+int metro_get_timings(const metro_ctx *ctx, metro_timings *out);
+
+/* Replaces ShiftHalosPartsGrids (+ SyncOrphanHalos) (src/utils.cpp:245-403,
+ * src/Communication.cpp:477-537): catalogue 1 becomes catalogue 0 on the device and the token
+ * halos of the last match are appended with their tuples (weight per prm->flavour). */
+int metro_shift(metro_ctx *ctx, const metro_params *prm);
+/* Read back catalogue `slot` halo table sizes / contents (after a shift the host needs the token
+ * halos it must append to locHalos[0]). */
+int metro_catalogue_info(metro_ctx *ctx, int slot, int64_t *n_halos, int64_t *n_tuples);
+int metro_catalogue_fetch_halos(metro_ctx *ctx, int slot, uint64_t *halo_id, int32_t *npart,
+				int32_t *n_orphan_steps, uint8_t *is_token);
+int metro_catalogue_fetch_tuples(metro_ctx *ctx, int slot, uint64_t *pid, uint32_t *halo, uint8_t *type);
+/* Overwrite Halo::nPart of a resident catalogue ([H * nptypes], host pointer).  Needed when the
+ * tuples of a catalogue are sharded over several GPUs by particle-ID range: the catalogue npart
+ * entering the merit is the halo's GLOBAL size, which only the caller can sum over the shards. */
+int metro_catalogue_set_npart(metro_ctx *ctx, int slot, const int32_t *npart);
+
+/* ---- building blocks exposed for tests / benchmarks ------------------------------------ */
+/* LSD radix sort of n u64 keys (optionally with u32 values) on bits [begin_bit, end_bit);
+ * device pointers; keys_out/vals_out receive the result; *_in are clobbered. */
+int metro_sort_u64(metro_ctx *ctx, uint64_t *keys_in, uint64_t *keys_out, uint32_t *vals_in,
+		   uint32_t *vals_out, int64_t n, int begin_bit, int end_bit);
+/* merit of MergerTree::SortByMerit computed ON THE DEVICE for n candidates (device arithmetic
+ * known-answer test; src/MergerTree.cpp:181-206).  Host pointers. */
+int metro_merit_bits(metro_ctx *ctx, int64_t n, const int32_t *n_comm, const int32_t *n_ph0,
+		     const int32_t *n_ph1, const int32_t *i_m, uint32_t *bits_out);
+
+/* ---- synthetic AHF-like catalogues, deterministic --------------- */
+typedef struct {
+	uint64_t seed;
+	int64_t n_halos;        /* halos of the later catalogue                                   */
+	int64_t n_tuples;       /* target tuples of the later catalogue (approximate)             */
+	int32_t pid_bits;       /* even; particle IDs are a Feistel permutation over 2^pid_bits   */
+	int32_t shard, n_shards;/* keep only pids whose top bits fall in this shard (pid range)   */
+} metro_synth_spec;
+/* Generates BOTH catalogues of a pair directly in HBM and installs them in slots 0 and 1. */
+int metro_synth_pair_device(metro_ctx *ctx, const metro_params *prm, const metro_synth_spec *spec);
+/* The same pair on the host (bit-identical tuples, possibly in a different order); two calls:
+ * sizes first (arrays NULL), then fill. */
+int metro_synth_pair_host(const metro_params *prm, const metro_synth_spec *spec, int slot,
+			  int64_t *n_halos, int64_t *n_tuples, uint64_t *halo_id, int32_t *npart,
+			  uint64_t *pid, uint32_t *halo, uint8_t *type);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,414 @@
+// capi.cu -- the extern "C" boundary (include/metro_b200.h) and the per-pair pipeline driver.
+#include "context.cuh"
+
+static char g_create_error[512] = "";
+
+void metro_set_error(metro_ctx *ctx, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	if (ctx) vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+	else vsnprintf(g_create_error, sizeof g_create_error, fmt, ap);
+	va_end(ap);
+}
+
+int dev_reserve(metro_ctx *ctx, DevBuf &b, size_t bytes)
+{
+	if (bytes <= b.cap && b.p) return METRO_OK;
+	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+	if (bytes < 256) bytes = 256;
+	CUDA_TRY(ctx, cudaMalloc(&b.p, bytes));
+	b.cap = bytes;
+	return METRO_OK;
+}
+
+void dev_free(DevBuf &b)
+{
+	if (b.p) cudaFree(b.p);
+	b.p = nullptr; b.cap = 0;
+}
+
+extern "C" {
+
+const char *metro_version(void) { return "metro-b200 0.1 (sm_100a)"; }
+
+const char *metro_last_error(const metro_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+
+int metro_ctx_create(int device, metro_ctx **out)
+{
+	if (!out) return METRO_ERR_INVALID;
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		metro_set_error(nullptr, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+		return METRO_ERR_CUDA;
+	}
+	if (device < 0 || device >= ndev) { metro_set_error(nullptr, "device %d out of range (%d visible)", device, ndev); return METRO_ERR_INVALID; }
+	cudaDeviceProp prop;
+	if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { metro_set_error(nullptr, "%s", cudaGetErrorString(e)); return METRO_ERR_CUDA; }
+	if (prop.major != 10) {
+		metro_set_error(nullptr, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+		return METRO_ERR_CUDA;
+	}
+	if ((e = cudaSetDevice(device)) != cudaSuccess) { metro_set_error(nullptr, "%s", cudaGetErrorString(e)); return METRO_ERR_CUDA; }
+	metro_ctx *ctx = new metro_ctx();
+	ctx->device = device;
+	memset(&ctx->timings, 0, sizeof ctx->timings);
+	memset(&ctx->res.info, 0, sizeof ctx->res.info);
+	bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+	for (int i = 0; ok && i < 16; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
+	for (int i = 0; ok && i < SORT_MAX_PASSES + 1; i++) ok = cudaEventCreate(&ctx->ev_pass[i]) == cudaSuccess;
+	ok = ok && cudaMallocHost(&ctx->h_counters, 64 * sizeof(u64)) == cudaSuccess;
+	ok = ok && dev_reserve(ctx, ctx->counters, 64 * sizeof(u64)) == METRO_OK;
+	if (!ok) {
+		metro_set_error(nullptr, "context setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+		delete ctx;
+		return METRO_ERR_CUDA;
+	}
+	*out = ctx;
+	return METRO_OK;
+}
+
+static void free_catalogue(DevCatalogue &c)
+{
+	DevBuf *b[] = {&c.halo_id, &c.npart, &c.npart_tot, &c.n_orphan_steps, &c.is_token, &c.pid, &c.halo, &c.type};
+	for (DevBuf *x : b) dev_free(*x);
+	c = DevCatalogue();
+}
+
+void metro_ctx_destroy(metro_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	free_catalogue(ctx->cat[0]); free_catalogue(ctx->cat[1]);
+	DevResult &r = ctx->res;
+	for (int d = 0; d < 2; d++) { dev_free(r.raw_off[d]); dev_free(r.raw_prog[d]); dev_free(r.raw_ncommon[d]); dev_free(r.raw_merit[d]); }
+	dev_free(r.tree_main); dev_free(r.tree_orphan); dev_free(r.tree_off); dev_free(r.clean_prog); dev_free(r.clean_ncommon); dev_free(r.token_halo);
+	sort_workspace_free(ctx->sortws);
+	dev_free(ctx->keys_a); dev_free(ctx->keys_b); dev_free(ctx->table); dev_free(ctx->scan_tmp); dev_free(ctx->counters);
+	for (DevBuf &b : ctx->scratch) dev_free(b);
+	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+	for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+	for (int i = 0; i < SORT_MAX_PASSES + 1; i++) cudaEventDestroy(ctx->ev_pass[i]);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+static int check_params(metro_ctx *ctx, const metro_params *prm)
+{
+	if (!prm) { metro_set_error(ctx, "params is NULL"); return METRO_ERR_INVALID; }
+	if (prm->nptypes < 1 || prm->nptypes > 8) { metro_set_error(ctx, "nptypes %d out of range 1..8", prm->nptypes); return METRO_ERR_INVALID; }
+	if (prm->fac_orphan_steps == 0) {
+		// the reference divides by facOrphanSteps (src/MergerTree.cpp:581): unset => SIGFPE there
+		metro_set_error(ctx, "facOrphanSteps must be non-zero");
+		return METRO_ERR_INVALID;
+	}
+	if (prm->flavour != METRO_FLAVOUR_GATHER && prm->flavour != METRO_FLAVOUR_ZOOM_DUP) { metro_set_error(ctx, "unknown flavour %d", prm->flavour); return METRO_ERR_INVALID; }
+	return METRO_OK;
+}
+
+static int upload_halos(metro_ctx *ctx, DevCatalogue &c, const metro_params *prm, const metro_catalogue *cat)
+{
+	const i64 H = cat->n_halos;
+	const int T = prm->nptypes;
+	cudaStream_t st = ctx->stream;
+	int rc;
+	if ((rc = dev_reserve(ctx, c.halo_id, (size_t) H * 8 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.npart, (size_t) H * T * 4 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.npart_tot, (size_t) H * 4 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.n_orphan_steps, (size_t) H * 4 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.is_token, (size_t) H + 8))) return rc;
+	if (H > 0) {
+		// Halo::nAllPart (src/Halo.cpp:63-70): plain int sum over the types
+		i32 *tot = (i32 *) malloc((size_t) H * 4);
+		if (!tot) { metro_set_error(ctx, "out of host memory"); return METRO_ERR_INVALID; }
+		for (i64 h = 0; h < H; h++) {
+			i32 s = 0;
+			for (int t = 0; t < T; t++) s += cat->npart[h * T + t];
+			tot[h] = s;
+		}
+		cudaError_t e = cudaMemcpyAsync(c.npart_tot.p, tot, (size_t) H * 4, cudaMemcpyHostToDevice, st);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+		free(tot);
+		CUDA_TRY(ctx, e);
+		CUDA_TRY(ctx, cudaMemcpyAsync(c.halo_id.p, cat->halo_id, (size_t) H * 8, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(ctx, cudaMemcpyAsync(c.npart.p, cat->npart, (size_t) H * T * 4, cudaMemcpyHostToDevice, st));
+		if (cat->n_orphan_steps) CUDA_TRY(ctx, cudaMemcpyAsync(c.n_orphan_steps.p, cat->n_orphan_steps, (size_t) H * 4, cudaMemcpyHostToDevice, st));
+		else CUDA_TRY(ctx, cudaMemsetAsync(c.n_orphan_steps.p, 0, (size_t) H * 4, st));
+		if (cat->is_token) CUDA_TRY(ctx, cudaMemcpyAsync(c.is_token.p, cat->is_token, (size_t) H, cudaMemcpyHostToDevice, st));
+		else CUDA_TRY(ctx, cudaMemsetAsync(c.is_token.p, 0, (size_t) H, st));
+	}
+	c.n_halos = H;
+	return METRO_OK;
+}
+
+static int check_catalogue(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat)
+{
+	int rc = check_params(ctx, prm);
+	if (rc) return rc;
+	if (slot < 0 || slot > 1 || !cat) { metro_set_error(ctx, "bad slot / NULL catalogue"); return METRO_ERR_INVALID; }
+	if (cat->n_halos < 0 || cat->n_tuples < 0 || cat->n_halos >= (1ll << 31)) { metro_set_error(ctx, "bad catalogue sizes"); return METRO_ERR_INVALID; }
+	if (cat->n_halos > 0 && (!cat->halo_id || !cat->npart)) { metro_set_error(ctx, "halo_id / npart is NULL"); return METRO_ERR_INVALID; }
+	if (cat->n_tuples > 0 && (!cat->pid || !cat->halo)) { metro_set_error(ctx, "pid / halo is NULL"); return METRO_ERR_INVALID; }
+	if (cat->n_tuples > 0 && cat->n_halos == 0) { metro_set_error(ctx, "tuples without halos"); return METRO_ERR_INVALID; }
+	return METRO_OK;
+}
+
+int metro_catalogue_upload(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat)
+{
+	if (!ctx) return METRO_ERR_INVALID;
+	int rc = check_catalogue(ctx, slot, prm, cat);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	DevCatalogue &c = ctx->cat[slot];
+	c.valid = false; c.b_pid = nullptr; c.b_halo = nullptr; c.b_type = nullptr;
+	if ((rc = upload_halos(ctx, c, prm, cat))) return rc;
+	const i64 N = cat->n_tuples;
+	cudaStream_t st = ctx->stream;
+	if ((rc = dev_reserve(ctx, c.pid, (size_t) N * 8 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.halo, (size_t) N * 4 + 8))) return rc;
+	if (cat->type) { if ((rc = dev_reserve(ctx, c.type, (size_t) N + 8))) return rc; }
+	else dev_free(c.type);
+	if (N > 0) {
+		CUDA_TRY(ctx, cudaMemcpyAsync(c.pid.p, cat->pid, (size_t) N * 8, cudaMemcpyHostToDevice, st));
+		CUDA_TRY(ctx, cudaMemcpyAsync(c.halo.p, cat->halo, (size_t) N * 4, cudaMemcpyHostToDevice, st));
+		if (cat->type) CUDA_TRY(ctx, cudaMemcpyAsync(c.type.p, cat->type, (size_t) N, cudaMemcpyHostToDevice, st));
+	}
+	c.n_tuples = N;
+	if ((rc = catalogue_scan_tuples(ctx, c, prm->nptypes))) return rc;
+	c.valid = true;
+	ctx->nptypes = prm->nptypes;
+	ctx->res.valid = false;
+	return METRO_OK;
+}
+
+int metro_catalogue_adopt_device(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat)
+{
+	if (!ctx) return METRO_ERR_INVALID;
+	int rc = check_catalogue(ctx, slot, prm, cat);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	DevCatalogue &c = ctx->cat[slot];
+	c.valid = false;
+	if ((rc = upload_halos(ctx, c, prm, cat))) return rc;
+	dev_free(c.pid); dev_free(c.halo); dev_free(c.type);
+	c.b_pid = cat->pid; c.b_halo = cat->halo; c.b_type = cat->type;
+	c.n_tuples = cat->n_tuples;
+	if (c.n_tuples == 0) { c.b_pid = nullptr; c.b_halo = nullptr; c.b_type = nullptr; }
+	if ((rc = catalogue_scan_tuples(ctx, c, prm->nptypes))) return rc;
+	c.valid = true;
+	ctx->nptypes = prm->nptypes;
+	ctx->res.valid = false;
+	return METRO_OK;
+}
+
+int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info *info)
+{
+	if (!ctx) return METRO_ERR_INVALID;
+	int rc = check_params(ctx, prm);
+	if (rc) return rc;
+	if (!ctx->cat[0].valid || !ctx->cat[1].valid) { metro_set_error(ctx, "both catalogues must be uploaded before metro_match_pair"); return METRO_ERR_STATE; }
+	if (prm->nptypes != ctx->nptypes) { metro_set_error(ctx, "nptypes differs from the uploaded catalogues"); return METRO_ERR_INVALID; }
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
+	const i64 N = c0.n_tuples + c1.n_tuples;
+	const i64 Hmax = std::max(c0.n_halos, c1.n_halos);
+	// key layout: pid | snap | halo | type must fit one u64 (see common.cuh)
+	int pid_bits = std::max(1, ceil_log2_u64(std::max(c0.max_pid, c1.max_pid)));
+	int halo_bits = std::max(1, ceil_log2_u64(Hmax > 0 ? (u64) (Hmax - 1) : 0));
+	int type_bits = prm->nptypes > 1 ? ceil_log2_u64((u64) prm->nptypes - 1) : 0;
+	if (pid_bits + 1 + halo_bits + type_bits > 64 || 2 * halo_bits + 2 * type_bits > 63) {
+		metro_set_error(ctx, "key does not fit 64 bits: pid %d + snap 1 + halo %d + type %d bits (wide-key path not built yet)",
+				pid_bits, halo_bits, type_bits);
+		return METRO_ERR_UNSUPPORTED;
+	}
+	const KeyLayout L = make_key_layout(pid_bits, halo_bits, type_bits);
+	const SortPlan plan = make_sort_plan(L.pid_shift, L.pid_shift + pid_bits);
+	DevResult &res = ctx->res;
+	res.valid = false;
+	memset(&res.info, 0, sizeof res.info);
+	res.info.n_halos[0] = c0.n_halos; res.info.n_halos[1] = c1.n_halos;
+	res.info.n_tuples[0] = c0.n_tuples; res.info.n_tuples[1] = c1.n_tuples;
+	res.info.pid_bits = pid_bits; res.info.halo_bits = halo_bits; res.info.type_bits = type_bits; res.info.sort_passes = plan.n_pass;
+	ctx->launches = 0;
+	memset(&ctx->timings, 0, sizeof ctx->timings);
+
+	if ((rc = dev_reserve(ctx, ctx->keys_a, (size_t) N * 8 + 16))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) N * 8 + 16))) return rc;
+	if ((rc = sort_workspace_reserve(ctx, ctx->sortws, N))) return rc;
+
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+	if ((rc = stage_pack_hist(ctx, L, plan))) return rc;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+	u64 *sorted = nullptr;
+	int sort_launches = 0;
+	if ((rc = sort_scatter_passes(ctx, st, ctx->sortws, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), nullptr, nullptr, N, plan, &sorted, nullptr,
+				      ctx->ev_pass, &sort_launches))) return rc;
+	ctx->launches += sort_launches;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+	i64 R = 0, hits = 0;
+	if ((rc = stage_join_count(ctx, L, sorted, N, &R, &hits))) return rc;
+	res.info.n_hits = hits;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
+	if ((rc = stage_select(ctx, prm, L, R))) return rc;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	metro_timings &tm = ctx->timings;
+	cudaEventElapsedTime(&tm.total, ctx->ev[0], ctx->ev[4]);
+	cudaEventElapsedTime(&tm.pack_hist, ctx->ev[0], ctx->ev[1]);
+	cudaEventElapsedTime(&tm.sort, ctx->ev[1], ctx->ev[2]);
+	cudaEventElapsedTime(&tm.join, ctx->ev[2], ctx->ev[3]);
+	cudaEventElapsedTime(&tm.select, ctx->ev[3], ctx->ev[4]);
+	if (N > 0) for (int p = 0; p < plan.n_pass; p++) cudaEventElapsedTime(&tm.sort_pass_ms[p], ctx->ev_pass[p], ctx->ev_pass[p + 1]);
+	tm.sort_launches = N > 0 ? plan.n_pass : 0;
+	tm.total_launches = ctx->launches;
+	res.valid = true;
+	if (info) *info = res.info;
+	return METRO_OK;
+}
+
+int metro_get_timings(const metro_ctx *ctx, metro_timings *out)
+{
+	if (!ctx || !out) return METRO_ERR_INVALID;
+	*out = ctx->timings;
+	return METRO_OK;
+}
+
+static int d2h(metro_ctx *ctx, void *dst, const DevBuf &src, size_t bytes)
+{
+	if (!dst || bytes == 0) return METRO_OK;
+	CUDA_TRY(ctx, cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	return METRO_OK;
+}
+
+int metro_result_fetch(metro_ctx *ctx, const metro_result_arrays *dst)
+{
+	if (!ctx || !dst) return METRO_ERR_INVALID;
+	if (!ctx->res.valid) { metro_set_error(ctx, "no result: call metro_match_pair first"); return METRO_ERR_STATE; }
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	DevResult &r = ctx->res;
+	const int T = ctx->nptypes;
+	int rc = 0;
+	for (int d = 0; d < 2 && !rc; d++) {
+		const size_t M = (size_t) r.info.raw_count[d];
+		rc = d2h(ctx, dst->raw_off[d], r.raw_off[d], (size_t) (r.info.n_halos[d] + 1) * 8);
+		if (!rc) rc = d2h(ctx, dst->raw_prog[d], r.raw_prog[d], M * 4);
+		if (!rc) rc = d2h(ctx, dst->raw_ncommon[d], r.raw_ncommon[d], M * T * 4);
+		if (!rc) rc = d2h(ctx, dst->raw_merit[d], r.raw_merit[d], M * 4);
+	}
+	if (!rc) rc = d2h(ctx, dst->tree_main, r.tree_main, (size_t) r.info.n_trees * 4);
+	if (!rc) rc = d2h(ctx, dst->tree_orphan, r.tree_orphan, (size_t) r.info.n_trees);
+	if (!rc) rc = d2h(ctx, dst->tree_off, r.tree_off, (size_t) (r.info.n_trees + 1) * 8);
+	if (!rc) rc = d2h(ctx, dst->clean_prog, r.clean_prog, (size_t) r.info.clean_count * 4);
+	if (!rc) rc = d2h(ctx, dst->clean_ncommon, r.clean_ncommon, (size_t) r.info.clean_count * T * 4);
+	if (!rc) rc = d2h(ctx, dst->token_halo, r.token_halo, (size_t) r.info.n_tokens * 4);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return METRO_OK;
+}
+
+int metro_shift(metro_ctx *ctx, const metro_params *prm)
+{
+	if (!ctx) return METRO_ERR_INVALID;
+	int rc = check_params(ctx, prm);
+	if (rc) return rc;
+	if (!ctx->res.valid) { metro_set_error(ctx, "metro_shift needs the result of metro_match_pair (token halos)"); return METRO_ERR_STATE; }
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	return stage_shift(ctx, prm);
+}
+
+int metro_catalogue_info(metro_ctx *ctx, int slot, int64_t *n_halos, int64_t *n_tuples)
+{
+	if (!ctx || slot < 0 || slot > 1) return METRO_ERR_INVALID;
+	if (!ctx->cat[slot].valid) { metro_set_error(ctx, "catalogue %d is empty", slot); return METRO_ERR_STATE; }
+	if (n_halos) *n_halos = ctx->cat[slot].n_halos;
+	if (n_tuples) *n_tuples = ctx->cat[slot].n_tuples;
+	return METRO_OK;
+}
+
+int metro_catalogue_fetch_halos(metro_ctx *ctx, int slot, uint64_t *halo_id, int32_t *npart, int32_t *n_orphan_steps, uint8_t *is_token)
+{
+	if (!ctx || slot < 0 || slot > 1) return METRO_ERR_INVALID;
+	DevCatalogue &c = ctx->cat[slot];
+	if (!c.valid) { metro_set_error(ctx, "catalogue %d is empty", slot); return METRO_ERR_STATE; }
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t H = (size_t) c.n_halos;
+	int rc = d2h(ctx, halo_id, c.halo_id, H * 8);
+	if (!rc) rc = d2h(ctx, npart, c.npart, H * ctx->nptypes * 4);
+	if (!rc) rc = d2h(ctx, n_orphan_steps, c.n_orphan_steps, H * 4);
+	if (!rc) rc = d2h(ctx, is_token, c.is_token, H);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return METRO_OK;
+}
+
+int metro_catalogue_fetch_tuples(metro_ctx *ctx, int slot, uint64_t *pid, uint32_t *halo, uint8_t *type)
+{
+	if (!ctx || slot < 0 || slot > 1) return METRO_ERR_INVALID;
+	DevCatalogue &c = ctx->cat[slot];
+	if (!c.valid) { metro_set_error(ctx, "catalogue %d is empty", slot); return METRO_ERR_STATE; }
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	const size_t N = (size_t) c.n_tuples;
+	if (N > 0) {
+		if (pid) CUDA_TRY(ctx, cudaMemcpyAsync(pid, c.d_pid(), N * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		if (halo) CUDA_TRY(ctx, cudaMemcpyAsync(halo, c.d_halo(), N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		if (type) {
+			if (c.d_type()) CUDA_TRY(ctx, cudaMemcpyAsync(type, c.d_type(), N, cudaMemcpyDeviceToHost, ctx->stream));
+			else memset(type, 1, N);
+		}
+	}
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return METRO_OK;
+}
+
+int metro_sort_u64(metro_ctx *ctx, uint64_t *keys_in, uint64_t *keys_out, uint32_t *vals_in, uint32_t *vals_out, int64_t n,
+		   int begin_bit, int end_bit)
+{
+	if (!ctx || n < 0 || begin_bit < 0 || end_bit > 64 || begin_bit > end_bit) return METRO_ERR_INVALID;
+	if (n > 0 && (!keys_in || !keys_out)) return METRO_ERR_INVALID;
+	if ((vals_in == nullptr) != (vals_out == nullptr)) return METRO_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	int rc = sort_workspace_reserve(ctx, ctx->sortws, n);
+	if (rc) return rc;
+	SortPlan plan = make_sort_plan(begin_bit, end_bit);
+	if ((rc = sort_clear_hist(ctx, st, ctx->sortws))) return rc;
+	if ((rc = sort_histogram(ctx, st, ctx->sortws, keys_in, n, plan))) return rc;
+	u64 *rk = nullptr; u32 *rv = nullptr;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[5], st));
+	if ((rc = sort_scatter_passes(ctx, st, ctx->sortws, keys_in, keys_out, vals_in, vals_out, n, plan, &rk, &rv, ctx->ev_pass, nullptr))) return rc;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[6], st));
+	if (n > 0 && rk != keys_out) {
+		CUDA_TRY(ctx, cudaMemcpyAsync(keys_out, rk, (size_t) n * 8, cudaMemcpyDeviceToDevice, st));
+		if (vals_in) CUDA_TRY(ctx, cudaMemcpyAsync(vals_out, rv, (size_t) n * 4, cudaMemcpyDeviceToDevice, st));
+	}
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	memset(&ctx->timings, 0, sizeof ctx->timings);
+	cudaEventElapsedTime(&ctx->timings.sort, ctx->ev[5], ctx->ev[6]);
+	if (n > 0) for (int p = 0; p < plan.n_pass; p++) cudaEventElapsedTime(&ctx->timings.sort_pass_ms[p], ctx->ev_pass[p], ctx->ev_pass[p + 1]);
+	ctx->timings.sort_launches = n > 0 ? plan.n_pass : 0;
+	return METRO_OK;
+}
+
+int metro_merit_bits(metro_ctx *ctx, int64_t n, const int32_t *n_comm, const int32_t *n_ph0, const int32_t *n_ph1, const int32_t *i_m,
+		     uint32_t *bits_out)
+{
+	if (!ctx || n < 0 || (n > 0 && (!n_comm || !n_ph0 || !n_ph1 || !i_m || !bits_out))) return METRO_ERR_INVALID;
+	if (n == 0) return METRO_OK;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	DevBuf *S = ctx->scratch;
+	int rc = 0;
+	for (int k = 0; k < 5 && !rc; k++) rc = dev_reserve(ctx, S[k], (size_t) n * 4);
+	if (rc) return rc;
+	const int32_t *src[4] = {n_comm, n_ph0, n_ph1, i_m};
+	for (int k = 0; k < 4; k++) CUDA_TRY(ctx, cudaMemcpyAsync(S[k].p, src[k], (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if ((rc = merit_bits_device(ctx, n, S[0].as<i32>(), S[1].as<i32>(), S[2].as<i32>(), S[3].as<i32>(), S[4].as<u32>()))) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(bits_out, S[4].p, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	return METRO_OK;
+}
+
+}  // extern "C"

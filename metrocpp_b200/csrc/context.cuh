@@ -1,0 +1,84 @@
+// context.cuh -- the engine context behind the C ABI (include/metro_b200.h).
+#pragma once
+#include <algorithm>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/metro_b200.h"
+#include "common.cuh"
+#include "radix_sort.cuh"
+
+// grow-only device buffer
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// One catalogue resident in HBM (SoA).  Replaces locHalos[i] + locMapParts[i] + locParts[i]
+// (reference src/global_vars.h:49-82).
+struct DevCatalogue {
+	i64 n_halos = 0, n_tuples = 0;
+	DevBuf halo_id;        // u64[H]
+	DevBuf npart;          // i32[H*T]
+	DevBuf npart_tot;      // i32[H]   sum over types (Halo::nAllPart)
+	DevBuf n_orphan_steps; // i32[H]
+	DevBuf is_token;       // u8[H]
+	DevBuf pid;            // u64[N]
+	DevBuf halo;           // u32[N]
+	DevBuf type;           // u8[N]
+	// borrowed tuple arrays (metro_catalogue_adopt_device); override pid/halo/type when set
+	const u64 *b_pid = nullptr;
+	const u32 *b_halo = nullptr;
+	const u8 *b_type = nullptr;
+	u64 max_pid = 0;
+	bool valid = false;
+	const u64 *d_pid() const { return b_pid ? b_pid : pid.as<u64>(); }
+	const u32 *d_halo() const { return b_pid ? b_halo : halo.as<u32>(); }
+	const u8 *d_type() const { return b_pid ? b_type : type.as<u8>(); }
+};
+
+// Result of the last match, resident in HBM (layout == metro_result_arrays).
+struct DevResult {
+	bool valid = false;
+	metro_result_info info;
+	DevBuf raw_off[2], raw_prog[2], raw_ncommon[2], raw_merit[2];
+	DevBuf tree_main, tree_orphan, tree_off, clean_prog, clean_ncommon, token_halo;
+};
+
+struct metro_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	char err[1024] = {0};
+	int nptypes = 0;
+	DevCatalogue cat[2];
+	DevResult res;
+	SortWorkspace sortws;
+	// scratch (grow-only)
+	DevBuf keys_a, keys_b;          // packed join keys, ping-pong
+	DevBuf table;                   // pair-count hash table
+	DevBuf scratch[64];             // select pipeline temporaries
+	DevBuf scan_tmp;                // block sums of the scan primitive
+	DevBuf counters;                // small device counters (u64[64])
+	u64 *h_counters = nullptr;      // pinned mirror
+	cudaEvent_t ev[16];
+	cudaEvent_t ev_pass[SORT_MAX_PASSES + 1];
+	metro_timings timings;
+	int launches = 0;
+};
+
+int dev_reserve(metro_ctx *ctx, DevBuf &b, size_t bytes);
+void dev_free(DevBuf &b);
+
+// ---- device primitives (scan.cu) ---------------------------------------------------------------
+// out[i] = sum_{j<i} in[j]  (u32 in, u32 out; in == out allowed); *total (device u64) = sum of all
+int scan_exclusive_u32(metro_ctx *ctx, cudaStream_t st, const u32 *in, u32 *out, i64 n, u64 *d_total);
+
+// ---- pipeline stages -----------------------------------------------------------------------------
+int stage_pack_hist(metro_ctx *ctx, const KeyLayout &L, const SortPlan &plan);      // join.cu
+int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 n,
+		     i64 *n_records, i64 *n_hits);                                     // join.cu
+int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &L, i64 n_records);   // select.cu
+int stage_shift(metro_ctx *ctx, const metro_params *prm);                            // shift.cu
+int merit_bits_device(metro_ctx *ctx, i64 n, const i32 *a, const i32 *b, const i32 *c, const i32 *d, u32 *out);   // select.cu
+int catalogue_scan_tuples(metro_ctx *ctx, DevCatalogue &c, int nptypes);             // shift.cu: max pid + validation

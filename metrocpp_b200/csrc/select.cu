@@ -1,0 +1,490 @@
+// select.cu -- from reduced pair counts to merger trees, entirely on the device.
+//
+// Replaces, for both directions at once:
+//   MergerTree::AssignMap     (reference src/MergerTree.cpp:133-169)  threshold, ascending-ID order
+//   MergerTree::SortByMerit   (src/MergerTree.cpp:174-244) + utils SortIndexes (src/utils.cpp:429-449)
+//   CleanTrees                (src/MergerTree.cpp:510-652)  mutual-best filter, orphan/token rule,
+//                                                           second merit sort
+// Work is O(M) with M = distinct (haloA, haloB) pairs (a few per halo), i.e. negligible next to
+// the tuple sort; every step is a flat data-parallel kernel, a scan or a small radix sort.
+#include "context.cuh"
+
+// ---- merit: bit-exact restatement of SortByMerit's arithmetic --------------------------------
+// fp32 divide of the int->float rounded sizes, then fp64 with NO fma contraction
+// (ratioM*1.01 - 1.0 must be a rounded multiply followed by a subtract), two roundings to fp32.
+__device__ __forceinline__ u32 merit_bits_dev(i32 nComm, i32 nPH0, i32 nPH1, i32 iM)
+{
+	const float q = __fdiv_rn(__int2float_rn(nPH0), __int2float_rn(nPH1));
+	double ratioM = (double) q;
+	if (ratioM < 1.0) ratioM = __ddiv_rn(1.0, ratioM);
+	const double den = __dsub_rn(__dmul_rn(ratioM, 1.01), 1.0);
+	float merit = __double2float_rn(__ddiv_rn((double) nComm, den));
+	const double fac = __dadd_rn(1.0, __dmul_rn(0.00001, (double) iM));
+	merit = __double2float_rn(__dmul_rn((double) merit, fac));
+	return __float_as_uint(merit);
+}
+
+// monotone map fp32 bits -> u32 (ascending); -0 is folded onto +0 like operator< does
+__device__ __forceinline__ u32 float_sortable(u32 b)
+{
+	if (b == 0x80000000u) b = 0;
+	return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void merit_test_kernel(i64 n, const i32 *a, const i32 *b, const i32 *c, const i32 *d, u32 *out)
+{
+	const i64 i = (i64) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = merit_bits_dev(a[i], b[i], c[i], d[i]);
+}
+
+int merit_bits_device(metro_ctx *ctx, i64 n, const i32 *a, const i32 *b, const i32 *c, const i32 *d, u32 *out)
+{
+	merit_test_kernel<<<(unsigned) div_up<i64>(n, 256), 256, 0, ctx->stream>>>(n, a, b, c, d, out);
+	CUDA_TRY(ctx, cudaGetLastError());
+	return METRO_OK;
+}
+
+// ---- small kernels -----------------------------------------------------------------------------
+#define TPB 256
+#define GRID(n) ((unsigned) div_up<i64>((n) > 0 ? (n) : 1, TPB))
+#define TID const i64 i = (i64) blockIdx.x * blockDim.x + threadIdx.x
+
+__global__ void iota_kernel(u32 *v, i64 n) { TID; if (i < n) v[i] = (u32) i; }
+__global__ void copy_u64_kernel(const u64 *a, u64 *b, i64 n) { TID; if (i < n) b[i] = a[i]; }
+__global__ void invert_perm_kernel(const u32 *rank2idx, u32 *rank, i64 n) { TID; if (i < n) rank[rank2idx[i]] = (u32) i; }
+
+struct HitLayout { int halo_bits, type_bits; };
+__device__ __forceinline__ void hit_decode(const HitLayout &h, u64 hk, u32 &A, u32 &B, u32 &tA, u32 &tB)
+{
+	const u32 tm = (1u << h.type_bits) - 1u;
+	tB = (u32) hk & tm;
+	tA = (u32) (hk >> h.type_bits) & tm;
+	const u64 hm = (1ull << h.halo_bits) - 1ull;
+	B = (u32) ((hk >> (2 * h.type_bits)) & hm);
+	A = (u32) ((hk >> (2 * h.type_bits + h.halo_bits)) & hm);
+}
+
+// record -> sort key (A, idRank1[B]) so that equal (A,B) are adjacent and B ascends by halo ID
+__global__ void rec_key_kernel(const u64 *rec, i64 n, HitLayout hl, const u32 *rank1, u64 *key, u32 *val)
+{
+	TID;
+	if (i >= n) return;
+	u32 A, B, tA, tB;
+	hit_decode(hl, rec[i], A, B, tA, tB);
+	key[i] = ((u64) A << 32) | rank1[B];
+	val[i] = (u32) i;
+}
+
+__global__ void head_flag_kernel(const u64 *key, i64 n, u32 *flag)
+{
+	TID;
+	if (i < n) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+}
+
+// merge the (tA,tB) records of one (A,B) pair: by-type counts for both directions
+__global__ void pair_merge_kernel(const u64 *rec, const u32 *rec_cnt, const u32 *order, const u32 *flag,
+				  const u32 *scan, i64 n, HitLayout hl, int T, u32 *pA, u32 *pB, i32 *pF, i32 *pK, i32 *ptot)
+{
+	TID;
+	if (i >= n) return;
+	const u32 r = order[i];
+	const u32 p = scan[i] + flag[i] - 1u;
+	u32 A, B, tA, tB;
+	hit_decode(hl, rec[r], A, B, tA, tB);
+	if (flag[i]) { pA[p] = A; pB[p] = B; }
+	const i32 c = (i32) rec_cnt[r];
+	atomicAdd(&pF[(i64) p * T + tB], c);      // forward tree: type on the catalogue-1 side
+	atomicAdd(&pK[(i64) p * T + tA], c);      // backward tree: type on the catalogue-0 side
+	atomicAdd(&ptot[p], c);
+}
+
+// AssignMap threshold: keep iff sum_t nCommon > minPartCmp (strict)
+__global__ void keep_flag_kernel(const i32 *ptot, i64 n, i32 min_part_cmp, u32 *flag)
+{
+	TID;
+	if (i < n) flag[i] = ptot[i] > min_part_cmp ? 1u : 0u;
+}
+
+__global__ void pair_compact_kernel(const u32 *flag, const u32 *scan, i64 n, int T, const u32 *pA, const u32 *pB,
+				    const i32 *pF, const i32 *pK, const i32 *ptot, u32 *kA, u32 *kB, i32 *kF, i32 *kK, i32 *ktot)
+{
+	TID;
+	if (i >= n || !flag[i]) return;
+	const u32 d = scan[i];
+	kA[d] = pA[i]; kB[d] = pB[i]; ktot[d] = ptot[i];
+	for (int t = 0; t < T; t++) { kF[(i64) d * T + t] = pF[i * T + t]; kK[(i64) d * T + t] = pK[i * T + t]; }
+}
+
+__global__ void count_by_kernel(const u32 *main, i64 n, u32 *cnt) { TID; if (i < n) atomicAdd(&cnt[main[i]], 1u); }
+
+// backward ordering key: (B, idRank0[A])
+__global__ void bwd_key_kernel(const u32 *kA, const u32 *kB, const u32 *rank0, i64 n, u64 *key, u32 *val)
+{
+	TID;
+	if (i < n) { key[i] = ((u64) kB[i] << 32) | rank0[kA[i]]; val[i] = (u32) i; }
+}
+
+__global__ void gather_dir_kernel(const u32 *perm, i64 n, int T, const u32 *src_main, const u32 *src_other, const i32 *src_nc,
+				  const i32 *src_tot, u32 *m_main, u32 *m_other, i32 *m_nc, i32 *m_tot)
+{
+	TID;
+	if (i >= n) return;
+	const u32 s = perm[i];
+	m_main[i] = src_main[s]; m_other[i] = src_other[s]; m_tot[i] = src_tot[s];
+	for (int t = 0; t < T; t++) m_nc[i * T + t] = src_nc[(i64) s * T + t];
+}
+
+// merit of element i (position iM inside its segment) and the (main, ~merit) sort key
+__global__ void merit_key_kernel(const u32 *m_main, const u32 *m_other, const i32 *m_tot, const u32 *segoff, const u32 *segcnt,
+				 const i32 *np_main, const i32 *np_other, i64 n, u32 *merit, u64 *key, u32 *val)
+{
+	TID;
+	if (i >= n) return;
+	const u32 a = m_main[i];
+	u32 mb = 0, low = 0;
+	if (segcnt[a] > 1) {
+		const i32 iM = (i32) ((u32) i - segoff[a]);
+		const i32 o = (i32) m_other[i];
+		mb = merit_bits_dev(m_tot[i], np_main[a], o >= 0 ? np_other[o] : np_main[a], iM);
+		low = ~float_sortable(mb);              // descending merit
+	}
+	merit[i] = mb;
+	key[i] = ((u64) a << 32) | low;
+	val[i] = (u32) i;
+}
+
+// SortIndexes tie quirk: inside a run of equal merits every position receives the run's first
+// element (lowest pre-sort index, which the stable sort put first).
+__global__ void tie_quirk_kernel(const u32 *sidx, const u32 *m_main, const u32 *merit, const u32 *segoff, i64 n, u32 *src)
+{
+	TID;
+	if (i >= n) return;
+	const u32 me = sidx[i];
+	const u32 a = m_main[me];
+	const u32 v = float_sortable(merit[me]);
+	i64 q = i;
+	const i64 lo = segoff[a];
+	while (q > lo && float_sortable(merit[sidx[q - 1]]) == v) q--;
+	src[i] = sidx[q];
+}
+
+__global__ void emit_raw_kernel(const u32 *src, i64 n, int T, const u32 *m_main, const u32 *m_other, const i32 *m_nc, const u32 *merit,
+				const u32 *segcnt, u32 *raw_main, i32 *raw_prog, i32 *raw_nc, u32 *raw_merit)
+{
+	TID;
+	if (i >= n) return;
+	const u32 s = src[i];
+	const u32 a = m_main[s];
+	raw_main[i] = a;
+	raw_prog[i] = (i32) m_other[s];
+	raw_merit[i] = segcnt[a] > 1 ? merit[s] : 0u;
+	for (int t = 0; t < T; t++) raw_nc[i * T + t] = m_nc[(i64) s * T + t];
+}
+
+__global__ void off32_to_64_kernel(const u32 *off, i64 n, u64 total, i64 *out)
+{
+	TID;
+	if (i < n) out[i] = off[i];
+	if (i == n) out[n] = (i64) total;
+}
+
+// best descendant of every catalogue-1 halo: head of its backward tree (-1 if none)
+__global__ void best_desc_kernel(const u32 *off1, const u32 *cnt1, const i32 *raw_prog1, i64 H1, i32 *best)
+{
+	TID;
+	if (i < H1) best[i] = cnt1[i] ? raw_prog1[off1[i]] : -1;
+}
+
+// mutual-best filter (CleanTrees :539-568): keep B iff ID(bestDesc[B]) == ID(A)
+__global__ void clean_flag_kernel(const u32 *raw_main0, const i32 *raw_prog0, i64 n, const i32 *best, const u64 *id0, u32 *flag, u32 *cntc)
+{
+	TID;
+	if (i >= n) return;
+	const u32 a = raw_main0[i];
+	const i32 d = best[raw_prog0[i]];
+	const u32 f = (d >= 0 && id0[d] == id0[a]) ? 1u : 0u;
+	flag[i] = f;
+	if (f) atomicAdd(&cntc[a], 1u);
+}
+
+// orphan / token rule (CleanTrees :575-617)
+__global__ void orphan_kernel(const u32 *cntc, const i32 *nptot0, const i32 *norph0, i64 H0, i32 min_part_halo, i32 fac, i32 maxs,
+			      u32 *token, u32 *nfin, u32 *has_tree, u64 *counters)
+{
+	TID;
+	if (i >= H0) return;
+	u32 tk = 0;
+	if (cntc[i] == 0 && nptot0[i] > min_part_halo) {
+		const i32 steps = norph0[i] + 1;
+		i32 loc = 1 + nptot0[i] / fac;
+		if (loc > maxs) loc = maxs;
+		if (steps <= loc) tk = 1;
+		else atomicAdd((unsigned long long *) &counters[4], 1ull);
+	}
+	token[i] = tk;
+	nfin[i] = cntc[i] + tk;
+	has_tree[i] = (cntc[i] + tk) > 0 ? 1u : 0u;
+}
+
+__global__ void clean_fill_kernel(const u32 *flag, const u32 *scan, i64 n, int T, const u32 *raw_main0, const i32 *raw_prog0,
+				  const i32 *raw_nc0, const u32 *cstart, const u32 *coff, u32 *c_main, u32 *c_other, i32 *c_nc, i32 *c_tot)
+{
+	TID;
+	if (i >= n || !flag[i]) return;
+	const u32 a = raw_main0[i];
+	const u32 d = coff[a] + (scan[i] - cstart[a]);
+	c_main[d] = a;
+	c_other[d] = (u32) raw_prog0[i];
+	i32 tot = 0;
+	for (int t = 0; t < T; t++) { i32 v = raw_nc0[i * T + t]; c_nc[(i64) d * T + t] = v; tot += v; }
+	c_tot[d] = tot;
+}
+
+__global__ void token_fill_kernel(const u32 *token, const u32 *coff, i64 H0, int T, const i32 *npart0, u32 *c_main, u32 *c_other,
+				  i32 *c_nc, i32 *c_tot)
+{
+	TID;
+	if (i >= H0 || !token[i]) return;
+	const u32 d = coff[i];
+	c_main[d] = (u32) i;
+	c_other[d] = 0xFFFFFFFFu;                   // -1: the token copy of the main halo itself
+	i32 tot = 0;
+	for (int t = 0; t < T; t++) { i32 v = npart0[i * T + t]; c_nc[(i64) d * T + t] = v; tot += v; }
+	c_tot[d] = tot;
+}
+
+__global__ void tree_emit_kernel(const u32 *has_tree, const u32 *tscan, const u32 *token, const u32 *coff, i64 H0, i32 *tree_main,
+				 u8 *tree_orphan, i64 *tree_off)
+{
+	TID;
+	if (i >= H0 || !has_tree[i]) return;
+	const u32 t = tscan[i];
+	tree_main[t] = (i32) i;
+	tree_orphan[t] = (u8) token[i];
+	tree_off[t] = coff[i];
+}
+
+__global__ void token_emit_kernel(const u32 *token, const u32 *kscan, i64 H0, i32 *token_halo)
+{
+	TID;
+	if (i < H0 && token[i]) token_halo[kscan[i]] = (i32) i;
+}
+
+__global__ void set_i64_kernel(i64 *p, i64 v) { *p = v; }
+
+// ---- host orchestration ------------------------------------------------------------------------
+#define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+#define RES(b, bytes) TRY(dev_reserve(ctx, (b), (size_t) (bytes) + 256))
+#define LAUNCHED() do { CUDA_TRY(ctx, cudaGetLastError()); ctx->launches++; } while (0)
+
+static int read_total(metro_ctx *ctx, const u64 *d, u64 *h)
+{
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 8, d, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	*h = ctx->h_counters[8];
+	return METRO_OK;
+}
+
+// key/value radix sort on bits [0, end_bit) using the four ping-pong buffers
+static int sort_kv(metro_ctx *ctx, u64 *ka, u64 *kb, u32 *va, u32 *vb, i64 n, int end_bit, u64 **rk, u32 **rv)
+{
+	cudaStream_t st = ctx->stream;
+	SortPlan plan = make_sort_plan(0, end_bit);
+	TRY(sort_workspace_reserve(ctx, ctx->sortws, n));
+	TRY(sort_clear_hist(ctx, st, ctx->sortws));
+	TRY(sort_histogram(ctx, st, ctx->sortws, ka, n, plan));
+	ctx->launches++;
+	return sort_scatter_passes(ctx, st, ctx->sortws, ka, kb, va, vb, n, plan, rk, rv, nullptr, &ctx->launches);
+}
+
+// argsort of the halo IDs of one catalogue: rank[h] = position of h in ascending-ID order
+static int id_ranks(metro_ctx *ctx, const DevCatalogue &c, DevBuf &rank_buf, DevBuf *tmp)
+{
+	cudaStream_t st = ctx->stream;
+	const i64 H = c.n_halos;
+	RES(rank_buf, H * 4);
+	if (H == 0) return METRO_OK;
+	RES(tmp[0], H * 8); RES(tmp[1], H * 8); RES(tmp[2], H * 4); RES(tmp[3], H * 4);
+	copy_u64_kernel<<<GRID(H), TPB, 0, st>>>(c.halo_id.as<u64>(), tmp[0].as<u64>(), H); LAUNCHED();
+	iota_kernel<<<GRID(H), TPB, 0, st>>>(tmp[2].as<u32>(), H); LAUNCHED();
+	u64 *rk; u32 *rv;
+	TRY(sort_kv(ctx, tmp[0].as<u64>(), tmp[1].as<u64>(), tmp[2].as<u32>(), tmp[3].as<u32>(), H, 64, &rk, &rv));
+	invert_perm_kernel<<<GRID(H), TPB, 0, st>>>(rv, rank_buf.as<u32>(), H); LAUNCHED();
+	return METRO_OK;
+}
+
+// Per-direction list (grouped by `main`, ascending ID of `other` inside a group) -> raw tree:
+// offsets per main halo, merit sort, tie quirk.  S = 8 scratch buffers.
+struct DirList { const u32 *main, *other; const i32 *nc, *tot; i64 n; };
+static int build_tree(metro_ctx *ctx, const DirList &L, i64 H_main, int T, const i32 *np_main, const i32 *np_other, int hbits,
+		      DevBuf *S, DevBuf &segcnt_b, DevBuf &segoff_b, DevBuf &out_main, DevBuf &out_prog, DevBuf &out_nc, DevBuf &out_merit)
+{
+	cudaStream_t st = ctx->stream;
+	const i64 n = L.n;
+	RES(segcnt_b, (H_main + 1) * 4); RES(segoff_b, (H_main + 1) * 4);
+	RES(out_main, n * 4); RES(out_prog, n * 4); RES(out_nc, n * T * 4); RES(out_merit, n * 4);
+	CUDA_TRY(ctx, cudaMemsetAsync(segcnt_b.p, 0, (size_t) (H_main + 1) * 4, st));
+	u32 *segcnt = segcnt_b.as<u32>(), *segoff = segoff_b.as<u32>();
+	if (n > 0) { count_by_kernel<<<GRID(n), TPB, 0, st>>>(L.main, n, segcnt); LAUNCHED(); }
+	TRY(scan_exclusive_u32(ctx, st, segcnt, segoff, H_main + 1, nullptr));
+	if (n == 0) return METRO_OK;
+	RES(S[0], n * 4); RES(S[1], n * 8); RES(S[2], n * 8); RES(S[3], n * 4); RES(S[4], n * 4); RES(S[5], n * 4);
+	u32 *merit = S[0].as<u32>();
+	merit_key_kernel<<<GRID(n), TPB, 0, st>>>(L.main, L.other, L.tot, segoff, segcnt, np_main, np_other, n, merit, S[1].as<u64>(), S[3].as<u32>());
+	LAUNCHED();
+	u64 *rk; u32 *sidx;
+	TRY(sort_kv(ctx, S[1].as<u64>(), S[2].as<u64>(), S[3].as<u32>(), S[4].as<u32>(), n, 32 + hbits, &rk, &sidx));
+	tie_quirk_kernel<<<GRID(n), TPB, 0, st>>>(sidx, L.main, merit, segoff, n, S[5].as<u32>()); LAUNCHED();
+	emit_raw_kernel<<<GRID(n), TPB, 0, st>>>(S[5].as<u32>(), n, T, L.main, L.other, L.nc, merit, segcnt, out_main.as<u32>(),
+						  out_prog.as<i32>(), out_nc.as<i32>(), out_merit.as<u32>());
+	LAUNCHED();
+	return METRO_OK;
+}
+
+int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, i64 R)
+{
+	cudaStream_t st = ctx->stream;
+	const int T = prm->nptypes;
+	DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
+	const i64 H0 = c0.n_halos, H1 = c1.n_halos;
+	DevBuf *S = ctx->scratch;        // [0]=rec_key [1]=rec_cnt (from stage_join_count)
+	DevResult &res = ctx->res;
+	u64 *cnt = ctx->counters.as<u64>();
+	HitLayout hl = {KL.halo_bits, KL.type_bits};
+	const int hbits = KL.halo_bits;
+	u64 tot = 0;
+
+	// halo-ID ranks (std::map iteration order of indexCommon is ascending halo ID, not file order)
+	TRY(id_ranks(ctx, c0, S[2], S + 40));
+	TRY(id_ranks(ctx, c1, S[3], S + 40));
+	const u32 *rank0 = S[2].as<u32>(), *rank1 = S[3].as<u32>();
+
+	// 1. order the records by (A, ID(B)) and merge the per-type records of each pair
+	i64 P = 0;
+	RES(S[4], R * 8); RES(S[5], R * 8); RES(S[6], R * 4); RES(S[7], R * 4); RES(S[8], R * 4); RES(S[9], R * 4);
+	u32 *order = nullptr;
+	if (R > 0) {
+		rec_key_kernel<<<GRID(R), TPB, 0, st>>>(S[0].as<u64>(), R, hl, rank1, S[4].as<u64>(), S[6].as<u32>()); LAUNCHED();
+		u64 *rk;
+		TRY(sort_kv(ctx, S[4].as<u64>(), S[5].as<u64>(), S[6].as<u32>(), S[7].as<u32>(), R, 32 + hbits, &rk, &order));
+		head_flag_kernel<<<GRID(R), TPB, 0, st>>>(rk, R, S[8].as<u32>()); LAUNCHED();
+		TRY(scan_exclusive_u32(ctx, st, S[8].as<u32>(), S[9].as<u32>(), R, cnt + 5));
+		TRY(read_total(ctx, cnt + 5, &tot));
+		P = (i64) tot;
+	}
+	res.info.n_pairs = P;
+	RES(S[10], P * 4); RES(S[11], P * 4); RES(S[12], P * T * 4); RES(S[13], P * T * 4); RES(S[14], P * 4);
+	i64 K = 0;
+	if (P > 0) {
+		CUDA_TRY(ctx, cudaMemsetAsync(S[12].p, 0, (size_t) P * T * 4, st));
+		CUDA_TRY(ctx, cudaMemsetAsync(S[13].p, 0, (size_t) P * T * 4, st));
+		CUDA_TRY(ctx, cudaMemsetAsync(S[14].p, 0, (size_t) P * 4, st));
+		pair_merge_kernel<<<GRID(R), TPB, 0, st>>>(S[0].as<u64>(), S[1].as<u32>(), order, S[8].as<u32>(), S[9].as<u32>(), R, hl, T,
+							    S[10].as<u32>(), S[11].as<u32>(), S[12].as<i32>(), S[13].as<i32>(), S[14].as<i32>());
+		LAUNCHED();
+		// 2. AssignMap threshold, ordered compaction
+		RES(S[15], P * 4); RES(S[16], P * 4);
+		keep_flag_kernel<<<GRID(P), TPB, 0, st>>>(S[14].as<i32>(), P, prm->min_part_cmp, S[15].as<u32>()); LAUNCHED();
+		TRY(scan_exclusive_u32(ctx, st, S[15].as<u32>(), S[16].as<u32>(), P, cnt + 5));
+		TRY(read_total(ctx, cnt + 5, &tot));
+		K = (i64) tot;
+	}
+	// kept pairs in forward order: kA S[17], kB S[18], kF S[19], kK S[20], ktot S[21]
+	RES(S[17], K * 4); RES(S[18], K * 4); RES(S[19], K * T * 4); RES(S[20], K * T * 4); RES(S[21], K * 4);
+	if (K > 0) {
+		pair_compact_kernel<<<GRID(P), TPB, 0, st>>>(S[15].as<u32>(), S[16].as<u32>(), P, T, S[10].as<u32>(), S[11].as<u32>(), S[12].as<i32>(),
+							      S[13].as<i32>(), S[14].as<i32>(), S[17].as<u32>(), S[18].as<u32>(), S[19].as<i32>(),
+							      S[20].as<i32>(), S[21].as<i32>());
+		LAUNCHED();
+	}
+
+	// 3. forward raw tree (locMTrees[0])
+	DirList fwd = {S[17].as<u32>(), S[18].as<u32>(), S[19].as<i32>(), S[21].as<i32>(), K};
+	TRY(build_tree(ctx, fwd, H0, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), hbits, S + 40, S[22], S[23], S[24], res.raw_prog[0],
+		       res.raw_ncommon[0], res.raw_merit[0]));
+	// 4. backward raw tree (locMTrees[1]): same pairs ordered by (B, ID(A)), by-type counts of the 0 side
+	RES(S[25], K * 4); RES(S[26], K * 4); RES(S[27], K * T * 4); RES(S[28], K * 4);
+	if (K > 0) {
+		RES(S[40], K * 8); RES(S[41], K * 8); RES(S[42], K * 4); RES(S[43], K * 4);
+		bwd_key_kernel<<<GRID(K), TPB, 0, st>>>(S[17].as<u32>(), S[18].as<u32>(), rank0, K, S[40].as<u64>(), S[42].as<u32>()); LAUNCHED();
+		u64 *rk; u32 *perm;
+		TRY(sort_kv(ctx, S[40].as<u64>(), S[41].as<u64>(), S[42].as<u32>(), S[43].as<u32>(), K, 32 + hbits, &rk, &perm));
+		gather_dir_kernel<<<GRID(K), TPB, 0, st>>>(perm, K, T, S[18].as<u32>(), S[17].as<u32>(), S[20].as<i32>(), S[21].as<i32>(),
+							    S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>());
+		LAUNCHED();
+	}
+	DirList bwd = {S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>(), K};
+	TRY(build_tree(ctx, bwd, H1, T, c1.npart_tot.as<i32>(), c0.npart_tot.as<i32>(), hbits, S + 40, S[29], S[30], S[31], res.raw_prog[1],
+		       res.raw_ncommon[1], res.raw_merit[1]));
+	res.info.raw_count[0] = res.info.raw_count[1] = K;
+	for (int d = 0; d < 2; d++) {
+		const i64 H = d ? H1 : H0;
+		RES(res.raw_off[d], (H + 1) * 8);
+		off32_to_64_kernel<<<GRID(H + 1), TPB, 0, st>>>((d ? S[30] : S[23]).as<u32>(), H, (u64) K, res.raw_off[d].as<i64>());
+		LAUNCHED();
+	}
+
+	// 5. CleanTrees: mutual-best filter
+	RES(S[32], (H1 + 1) * 4);
+	best_desc_kernel<<<GRID(H1), TPB, 0, st>>>(S[30].as<u32>(), S[29].as<u32>(), res.raw_prog[1].as<i32>(), H1, S[32].as<i32>()); LAUNCHED();
+	RES(S[33], K * 4); RES(S[34], K * 4); RES(S[35], (H0 + 1) * 4); RES(S[36], (H0 + 1) * 4);
+	u32 *cntc = S[35].as<u32>(), *cstart = S[36].as<u32>();
+	CUDA_TRY(ctx, cudaMemsetAsync(cntc, 0, (size_t) (H0 + 1) * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(cnt + 4, 0, sizeof(u64), st));
+	if (K > 0) {
+		clean_flag_kernel<<<GRID(K), TPB, 0, st>>>(S[24].as<u32>(), res.raw_prog[0].as<i32>(), K, S[32].as<i32>(), c0.halo_id.as<u64>(),
+							    S[33].as<u32>(), cntc);
+		LAUNCHED();
+		TRY(scan_exclusive_u32(ctx, st, S[33].as<u32>(), S[34].as<u32>(), K, nullptr));
+	}
+	TRY(scan_exclusive_u32(ctx, st, cntc, cstart, H0 + 1, nullptr));
+	// orphan / token rule
+	RES(S[37], (H0 + 1) * 4); RES(S[38], (H0 + 1) * 4); RES(S[39], (H0 + 1) * 4);
+	u32 *token = S[37].as<u32>(), *nfin = S[38].as<u32>(), *has_tree = S[39].as<u32>();
+	CUDA_TRY(ctx, cudaMemsetAsync(token, 0, (size_t) (H0 + 1) * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(nfin, 0, (size_t) (H0 + 1) * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(has_tree, 0, (size_t) (H0 + 1) * 4, st));
+	if (H0 > 0) {
+		orphan_kernel<<<GRID(H0), TPB, 0, st>>>(cntc, c0.npart_tot.as<i32>(), c0.n_orphan_steps.as<i32>(), H0, prm->min_part_halo,
+							 prm->fac_orphan_steps, prm->max_orphan_steps, token, nfin, has_tree, cnt);
+		LAUNCHED();
+	}
+	DevBuf *Q = S + 48;              // second scratch bank
+	RES(Q[0], (H0 + 1) * 4); RES(Q[1], (H0 + 1) * 4); RES(Q[2], (H0 + 1) * 4);
+	u32 *coff = Q[0].as<u32>(), *tscan = Q[1].as<u32>(), *kscan = Q[2].as<u32>();
+	TRY(scan_exclusive_u32(ctx, st, nfin, coff, H0 + 1, cnt + 5));
+	TRY(scan_exclusive_u32(ctx, st, has_tree, tscan, H0 + 1, cnt + 6));
+	TRY(scan_exclusive_u32(ctx, st, token, kscan, H0 + 1, cnt + 7));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, cnt, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	const i64 C = (i64) ctx->h_counters[5], NT = (i64) ctx->h_counters[6], NK = (i64) ctx->h_counters[7];
+	res.info.n_untracked = (i64) ctx->h_counters[4];
+	res.info.clean_count = C; res.info.n_trees = NT; res.info.n_tokens = NK;
+
+	// clean list grouped by A (kept entries in first-sort order, or the single token entry)
+	RES(Q[3], C * 4); RES(Q[4], C * 4); RES(Q[5], C * T * 4); RES(Q[6], C * 4);
+	if (K > 0) {
+		clean_fill_kernel<<<GRID(K), TPB, 0, st>>>(S[33].as<u32>(), S[34].as<u32>(), K, T, S[24].as<u32>(), res.raw_prog[0].as<i32>(),
+							    res.raw_ncommon[0].as<i32>(), cstart, coff, Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(),
+							    Q[6].as<i32>());
+		LAUNCHED();
+	}
+	if (H0 > 0) {
+		token_fill_kernel<<<GRID(H0), TPB, 0, st>>>(token, coff, H0, T, c0.npart.as<i32>(), Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(),
+							     Q[6].as<i32>());
+		LAUNCHED();
+	}
+	// second SortByMerit (:627-628) with iM = position in the kept list
+	DirList cl = {Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(), Q[6].as<i32>(), C};
+	TRY(build_tree(ctx, cl, H0, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), hbits, S + 40, Q[7], Q[8], Q[9], res.clean_prog,
+		       res.clean_ncommon, Q[10]));
+	RES(res.tree_main, NT * 4); RES(res.tree_orphan, NT); RES(res.tree_off, (NT + 1) * 8); RES(res.token_halo, NK * 4);
+	if (H0 > 0) {
+		tree_emit_kernel<<<GRID(H0), TPB, 0, st>>>(has_tree, tscan, token, coff, H0, res.tree_main.as<i32>(), res.tree_orphan.as<u8>(),
+							    res.tree_off.as<i64>());
+		LAUNCHED();
+		token_emit_kernel<<<GRID(H0), TPB, 0, st>>>(token, kscan, H0, res.token_halo.as<i32>()); LAUNCHED();
+	}
+	set_i64_kernel<<<1, 1, 0, st>>>(res.tree_off.as<i64>() + NT, C); LAUNCHED();
+	return METRO_OK;
+}
