@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py -- progenitor matching of one snapshot pair (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                 # our arm, 1 B200
+    torchrun ... bench.py --gpus N ...                            # one rank per GPU (pid-range shards)
+    python bench.py --impl reference ...                          # the reference's CPU path on the host cores
+
+A "step" is ONE pass of the hot path over one synthetic snapshot pair: pack -> radix sort ->
+run-length join -> pair-count reduce -> selection (forward + backward trees, mutual-best filter,
+orphan/token rule), device-resident tuples in, device-resident assignments out.
+metric = bound particle IDs matched per second per pair = (N_A + N_B) / t_pair.
+
+Workload at N=1: configs[1] of BASELINE.json, the synthetic 1024^3 full-box pair (1e6 halos,
+5e8 bound IDs per snapshot, dense pids < 2^30).  N>1: the same per-GPU volume, sharded by
+particle-ID range (weak scaling; N=8 is configs[2], the 2048^3 pair).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "bound particle IDs matched/sec per snapshot pair"
+UNIT = "IDs/s"
+FALLBACK_HBM_GBS = 6650.0          # B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--halos", type=int, default=1_000_000, help="halos per snapshot per GPU")
+    ap.add_argument("--tuples", type=int, default=500_000_000, help="bound IDs per snapshot per GPU")
+    ap.add_argument("--pid-bits", type=int, default=0, help="0 = smallest even width that fits")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="tuples per snapshot of the CPU sample")
+    ap.add_argument("--ref-sample", type=int, default=400_000)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe) sampled DURING the timed region
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic_per_launch():
+    """dram read+write bytes per onesweep launch from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            d = json.load(f)
+        return d.get("onesweep_dram_bytes_per_key")
+    except Exception:
+        return None
+
+
+def pick_pid_bits(tuples_total_one_snapshot: int) -> int:
+    # ranks ~ tuples/1.15; the generator needs 2 x ranks <= 2^bits, bits even
+    need = 2 * int(tuples_total_one_snapshot / 1.10) + 16
+    b = max(8, need.bit_length())
+    return b + (b & 1)
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm helpers: reference binary (oracle/_ref, built from /root/reference in the build
+# container; the binaries travel with the repo snapshot) or the C restatement.
+def host_catalogue_to_snapshot(cat, number, redshift):
+    """lib host catalogue -> AHF snapshot (tuples grouped by halo, empty halos dropped: the
+    reference's _particles parser cannot represent a 0-particle halo)."""
+    import numpy as np
+    from oracle.ahf_io import Snapshot
+    order = np.argsort(cat.halo, kind="stable")
+    halo = cat.halo[order]
+    counts = np.bincount(halo, minlength=cat.n_halos)
+    keep = counts > 0
+    offsets = np.zeros(int(keep.sum()) + 1, np.int64)
+    np.cumsum(counts[keep], out=offsets[1:])
+    typ = cat.type[order] if cat.type is not None else np.ones(halo.shape[0], np.uint8)
+    return Snapshot(number, redshift, cat.halo_id[keep], cat.npart.sum(axis=1)[keep].astype(np.int32), offsets,
+                    cat.pid[order], typ)
+
+
+def cpu_sample_pair(seed, tuples):
+    import metrocpp_b200 as mb
+    halos = max(50, tuples // 500)
+    prm = mb.make_params(nptypes=2)
+    spec = mb.SynthSpec(seed=seed, n_halos=halos, n_tuples=tuples, pid_bits=pick_pid_bits(tuples), shard=0, n_shards=1)
+    c0, c1 = mb.synth_pair_host(prm, spec, 0), mb.synth_pair_host(prm, spec, 1)
+    return [host_catalogue_to_snapshot(c1, 1, 0.100), host_catalogue_to_snapshot(c0, 2, 0.000)], halos
+
+
+def ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "MetroCPP_zoom")
+    return p if os.path.isfile(p) and os.access(p, os.X_OK) else None
+
+
+def prepare_ref_run(work, snaps):
+    """Lay out one reference run.  The snapshot lists the reference normally obtains from
+    scripts/find_*.sh are pre-seeded in tmp/output_*.tmp (it reuses them when present,
+    reference src/IOSettings.cpp:253-262), so nothing under /root/reference is needed."""
+    from oracle import ahf_io, run_ref
+    metro, inp, out = (os.path.join(work, d) for d in ("metro", "input", "output"))
+    for d in (os.path.join(metro, "tmp"), os.path.join(metro, "data"), os.path.join(metro, "scripts"), inp, out):
+        os.makedirs(d, exist_ok=True)
+    ss = sorted(snaps, key=lambda s: s.number)
+    for s in ss:
+        ahf_io.write_snapshot(inp, s, with_types=False)
+    with open(os.path.join(metro, "tmp", "output_n.tmp"), "w") as f:
+        f.write(f"{len(ss)}\n")
+    with open(os.path.join(metro, "tmp", "output_id.tmp"), "w") as f:
+        f.write("".join(f"{s.number:03d}\n" for s in ss))
+    with open(os.path.join(metro, "tmp", "output_z.tmp"), "w") as f:
+        f.write("".join(f"{s.redshift:.3f}\n" for s in ss))
+    # a(t) / P(k) tables: loaded into splines at start-up (the spline asserts on < 3 points) and never
+    # evaluated by the matching path: placeholder tables suffice.
+    with open(os.path.join(metro, "data", "a2t_5Myr_planck.dat"), "w") as f:
+        f.write("".join(f"{0.01 + 0.099 * i:.6f}\n" for i in range(11)))
+    with open(os.path.join(metro, "data", "pk_planck.dat"), "w") as f:
+        f.write("".join(f"{1e-4 * 2 ** i:.8g} {100.0 + i:.6g}\n" for i in range(11)))
+    cfg = os.path.join(work, "config.cfg")
+    run_ref.write_config(cfg, metro=metro, inp=inp, out=out, n_snaps=len(ss), fullbox=False,
+                         params=dict(minPartHalo=30, minPartCmp=10, facOrphanSteps=15, maxOrphanSteps=None))
+    return cfg
+
+
+def parse_ref_times(stdout):
+    fw = re.search(r"forwards\.\.\.done in ([0-9.eE+-]+)s", stdout)
+    bw = re.search(r"backwards\.\.\.done in ([0-9.eE+-]+)s", stdout)
+    if not fw or not bw:
+        raise RuntimeError("could not parse the reference's timing lines:\n" + stdout[-2000:])
+    return float(fw.group(1)), float(bw.group(1))
+
+
+def run_ref_instances(cfgs, works):
+    """Run len(cfgs) single-rank reference processes concurrently; returns [(fwd_s, bwd_s)]."""
+    procs = [subprocess.Popen([ref_binary(), c], cwd=w, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for c, w in zip(cfgs, works)]
+    outs = [p.communicate()[0] for p in procs]
+    return [parse_ref_times(o) for o in outs]
+
+
+def time_oracle_port(snaps):
+    from oracle import binding
+    prm = binding.Params(2, 10, 30, 15, 0, binding.FLAVOUR_ZOOM_DUP)
+    ss = sorted(snaps, key=lambda s: -s.number)
+    c0 = binding.catalogue_from_snapshot(ss[0], 2, True)
+    c1 = binding.catalogue_from_snapshot(ss[1], 2, True)
+    t0 = time.perf_counter()
+    binding.match_pair(prm, c0, c1)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(sample_tuples):
+    """One core, one bounded sample of the same synthetic workload."""
+    snaps, halos = cpu_sample_pair(4242, sample_tuples)
+    n_ids = sum(s.n_tuples for s in snaps)
+    desc = f"synthetic pair, {halos} halos, {n_ids} bound IDs (same generator as the GPU workload)"
+    if ref_binary():
+        work = tempfile.mkdtemp(prefix="metro_cpu_")
+        try:
+            cfg = prepare_ref_run(work, snaps)
+            (fw, bw), = run_ref_instances([cfg], [work])
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        return {"value": n_ids / (fw + bw), "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": desc + "; compiled reference (ZOOM build, 1 rank), FindProgenitors fwd+bwd CPU seconds",
+                "seconds": fw + bw}
+    t = time_oracle_port(snaps)
+    return {"value": n_ids / t, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": desc + "; C restatement (oracle/metro_oracle.c), match_pair wall seconds", "seconds": t}
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cores = max(1, min(cores, 32))
+    works, cfgs, ids = [], [], 0
+    kind = "reference" if ref_binary() else "port"
+    sample_sets = []
+    for i in range(cores):
+        snaps, halos = cpu_sample_pair(1000 + i, args.ref_sample)
+        sample_sets.append(snaps)
+        ids += sum(s.n_tuples for s in snaps)
+        if kind == "reference":
+            w = tempfile.mkdtemp(prefix=f"metro_ref{i}_")
+            works.append(w)
+            cfgs.append(prepare_ref_run(w, snaps))
+    rates = []
+    try:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            if kind == "reference":
+                times = run_ref_instances(cfgs, works)
+                rate = sum(sum(s.n_tuples for s in ss) / (fw + bw) for ss, (fw, bw) in zip(sample_sets, times))
+            else:
+                import concurrent.futures as cf
+                with cf.ThreadPoolExecutor(cores) as ex:
+                    ts = list(ex.map(time_oracle_port, sample_sets))
+                rate = sum(sum(s.n_tuples for s in ss) / t for ss, t in zip(sample_sets, ts))
+            if step >= args.warmup:
+                rates.append((rate, time.perf_counter() - t0))
+    finally:
+        for w in works:
+            shutil.rmtree(w, ignore_errors=True)
+    value = statistics.mean(r for r, _ in rates)
+    ms = statistics.mean(t for _, t in rates) * 1e3
+    sample = (f"{cores} concurrent single-rank instances (no MPI runtime on the box), each a synthetic pair of "
+              f"{args.ref_sample} bound IDs per snapshot; rate = sum over instances of (N_A+N_B)/(fwd+bwd seconds)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "synthetic 1024^3 full-box snapshot pair (bounded CPU sample of it)", "sample_ids_per_step": ids},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import metrocpp_b200 as mb
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    H_glob, N_glob = args.halos * world, args.tuples * world
+    pid_bits = args.pid_bits or pick_pid_bits(N_glob)
+    prm = mb.make_params(nptypes=2, min_part_cmp=10, min_part_halo=100, fac_orphan_steps=100, max_orphan_steps=15,
+                         flavour=mb.FLAVOUR_GATHER)          # config/fullbox_*.cfg settings
+    spec = mb.SynthSpec(seed=20261019, n_halos=H_glob, n_tuples=N_glob, pid_bits=pid_bits, shard=rank, n_shards=world)
+    eng = mb.MetroEngine(local_rank)
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    eng.synth_pair_device(prm, spec)
+    if world > 1:
+        # catalogue npart of the earlier halos = sum over the pid shards
+        c1 = eng.fetch_catalogue(1, tuples=False)
+        t = torch.from_numpy(c1.npart.astype(np.int32)).to(dev)
+        dist.all_reduce(t)
+        eng.set_npart(1, t.cpu().numpy())
+    n0 = eng.catalogue_sizes(0)[1]
+    n1 = eng.catalogue_sizes(1)[1]
+    ids_local = n0 + n1
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step():
+        return eng.match_pair(prm)
+
+    for _ in range(args.warmup):
+        info = step()
+    # ---- timed region: K steps, device events on the launching stream
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pass_ms, stage = [], {"pack_hist": 0.0, "sort": 0.0, "join": 0.0, "select": 0.0}
+    launches = 0
+    ev0.record(stream)
+    for _ in range(args.steps):
+        info = step()
+        t = eng.timings()
+        pass_ms += t["sort_pass_ms"][: t["sort_launches"]]
+        for k in stage:
+            stage[k] += t[k]
+        launches += t["total_launches"]
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    tt = torch.tensor([ms_total, float(ids_local)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, ids_glob = float(mx[0]), float(sm[1])
+    else:
+        ids_glob = float(ids_local)
+    ms_per_step = ms_total / args.steps
+    value = ids_glob / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (onesweep scatter pass): 8 B read + 8 B written per key
+    peak, peak_src = measured_hbm_peak()
+    avg_pass_ms = statistics.mean(pass_ms) if pass_ms else float("nan")
+    bytes_per_launch = 16.0 * ids_local
+    achieved = bytes_per_launch / (avg_pass_ms * 1e-3) / 1e9
+    per_key = ncu_traffic_per_launch()
+    roofline = {"bound": "hbm", "kernel": "onesweep_kernel<false,u32> (one LSD pass over the packed u64 keys)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "traffic": per_key * ids_local if per_key else None,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_pass_ms,
+                "launches_per_step": info["sort_passes"],
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}}
+
+    # ---- e2e: the user-facing call sequence with HOST buffers: upload both catalogues from pinned
+    # memory, match, fetch the clean trees.
+    e2e = None
+    if not args.no_e2e:
+        e2e = measure_e2e(eng, prm, dev, dist, max(1, min(args.steps, 3)), ids_glob)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": ("synthetic 1024^3 full-box snapshot pair" if world == 1 else
+                                    f"synthetic full-box snapshot pair sharded by particle-ID range over {world} GPUs"),
+                       "halos_per_snapshot": H_glob, "bound_ids_per_snapshot": int(ids_glob / 2), "pid_bits": info["pid_bits"],
+                       "sort_passes": info["sort_passes"], "l2": "inputs (>= 8 GB of keys per pass) far exceed the 126 MB L2",
+                       "params": "minPartCmp=10 minPartHalo=100 facOrphanSteps=100 maxOrphanSteps=15 (fullbox cfg)",
+                       "n_hits": info["n_hits"], "n_pairs": info["n_pairs"], "n_trees": info["n_trees"],
+                       "n_tokens": info["n_tokens"]},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
+    if e2e:
+        line["e2e"] = e2e
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+            except Exception as ex:                      # never lose the GPU line over the CPU leg
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {ex}"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
+    import numpy as np
+    import torch
+    import metrocpp_b200 as mb
+    stream = torch.cuda.current_stream(dev)
+    cats = []
+    for slot in range(2):
+        H, N = eng.catalogue_sizes(slot)
+        halos = eng.fetch_catalogue(slot, tuples=False)
+        pid = torch.empty(N, dtype=torch.int64, pin_memory=True)
+        halo = torch.empty(N, dtype=torch.int32, pin_memory=True)
+        rc = eng.lib.metro_catalogue_fetch_tuples(eng.h, slot, pid.data_ptr(), halo.data_ptr(), None)
+        eng._check(rc)
+        cats.append((halos, pid, halo))
+    h2d = sum(p.numel() * 8 + h.numel() * 4 + c.n_halos * (8 + 4 * prm.nptypes + 4 + 1) for c, p, h in cats)
+
+    def one():
+        for slot, (c, pid, halo) in enumerate(cats):
+            hc = mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, pid.numpy().view(np.uint64),
+                                  halo.numpy().view(np.uint32), None)
+            eng.upload(slot, prm, hc)
+        info = eng.match_pair(prm)
+        res = eng.fetch_result(info, raw=False)
+        d2h = res.tree_main.nbytes + res.tree_orphan.nbytes + res.tree_off.nbytes + res.clean_prog.nbytes + \
+            res.clean_ncommon.nbytes + res.token_halo.nbytes
+        return d2h
+
+    one()                                                   # warm-up (allocations)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        d2h = one()
+    ev1.record(stream)
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    ms = max(ev0.elapsed_time(ev1), wall * 1e3)             # host work (packing structs) counts too
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return {"value": ids_glob / (ms / steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": ms / steps, "steps": steps,
+            "path": "metro_catalogue_upload x2 (pinned host SoA) -> metro_match_pair -> metro_result_fetch (clean trees)"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,9 @@ typedef struct {
 int metro_ctx_create(int device, metro_ctx **out);
 void metro_ctx_destroy(metro_ctx *ctx);
 const char *metro_last_error(const metro_ctx *ctx);   /* ctx may be NULL: last create error */
+/* Run all work of this context on the caller's CUDA stream (a cudaStream_t, e.g. the stream the
+ * caller's own events are recorded on); NULL restores the context's private stream. */
+int metro_ctx_set_stream(metro_ctx *ctx, void *cuda_stream);
 const char *metro_version(void);
 
 /* ---- catalogues ---------------------------------------------------------------------- */

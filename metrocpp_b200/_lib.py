@@ -59,6 +59,7 @@ SYMBOLS = {
     "metro_ctx_destroy": (None, [_P]),
     "metro_last_error": (C.c_char_p, [_P]),
     "metro_version": (C.c_char_p, []),
+    "metro_ctx_set_stream": (C.c_int, [_P, _P]),
     "metro_catalogue_upload": (C.c_int, [_P, C.c_int, C.POINTER(Params), C.POINTER(Catalogue)]),
     "metro_catalogue_adopt_device": (C.c_int, [_P, C.c_int, C.POINTER(Params), C.POINTER(Catalogue)]),
     "metro_match_pair": (C.c_int, [_P, C.POINTER(Params), C.POINTER(ResultInfo)]),

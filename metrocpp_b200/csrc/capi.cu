@@ -56,7 +56,8 @@ int metro_ctx_create(int device, metro_ctx **out)
 	ctx->device = device;
 	memset(&ctx->timings, 0, sizeof ctx->timings);
 	memset(&ctx->res.info, 0, sizeof ctx->res.info);
-	bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+	bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+	ctx->stream = ctx->own_stream;
 	for (int i = 0; ok && i < 16; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
 	for (int i = 0; ok && i < SORT_MAX_PASSES + 1; i++) ok = cudaEventCreate(&ctx->ev_pass[i]) == cudaSuccess;
 	ok = ok && cudaMallocHost(&ctx->h_counters, 64 * sizeof(u64)) == cudaSuccess;
@@ -67,6 +68,15 @@ int metro_ctx_create(int device, metro_ctx **out)
 		return METRO_ERR_CUDA;
 	}
 	*out = ctx;
+	return METRO_OK;
+}
+
+int metro_ctx_set_stream(metro_ctx *ctx, void *cuda_stream)
+{
+	if (!ctx) return METRO_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
 	return METRO_OK;
 }
 
@@ -92,7 +102,7 @@ void metro_ctx_destroy(metro_ctx *ctx)
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
 	for (int i = 0; i < SORT_MAX_PASSES + 1; i++) cudaEventDestroy(ctx->ev_pass[i]);
-	cudaStreamDestroy(ctx->stream);
+	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
 

@@ -48,7 +48,8 @@ struct DevResult {
 
 struct metro_ctx {
 	int device = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr;       // stream in use
+	cudaStream_t own_stream = nullptr;   // the context's private stream
 	char err[1024] = {0};
 	int nptypes = 0;
 	DevCatalogue cat[2];

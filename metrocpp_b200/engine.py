@@ -91,6 +91,10 @@ class MetroEngine:
         except Exception:
             pass
 
+    def set_stream(self, cuda_stream: int | None):
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self.lib.metro_ctx_set_stream(self.h, cuda_stream))
+
     def _check(self, rc):
         if rc != 0:
             raise MetroError(rc, self.lib.metro_last_error(self.h).decode())
