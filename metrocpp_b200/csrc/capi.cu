@@ -97,7 +97,7 @@ void metro_ctx_destroy(metro_ctx *ctx)
 	for (int d = 0; d < 2; d++) { dev_free(r.raw_off[d]); dev_free(r.raw_prog[d]); dev_free(r.raw_ncommon[d]); dev_free(r.raw_merit[d]); }
 	dev_free(r.tree_main); dev_free(r.tree_orphan); dev_free(r.tree_off); dev_free(r.clean_prog); dev_free(r.clean_ncommon); dev_free(r.token_halo);
 	sort_workspace_free(ctx->sortws);
-	dev_free(ctx->keys_a); dev_free(ctx->keys_b); dev_free(ctx->table); dev_free(ctx->scan_tmp); dev_free(ctx->counters);
+	dev_free(ctx->keys_a); dev_free(ctx->keys_b); dev_free(ctx->table); dev_free(ctx->pair_cache); dev_free(ctx->scan_tmp); dev_free(ctx->counters);
 	for (DevBuf &b : ctx->scratch) dev_free(b);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);

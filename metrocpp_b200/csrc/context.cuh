@@ -57,7 +57,8 @@ struct metro_ctx {
 	SortWorkspace sortws;
 	// scratch (grow-only)
 	DevBuf keys_a, keys_b;          // packed join keys, ping-pong
-	DevBuf table;                   // pair-count hash table
+	DevBuf table;                   // pair-count hash table (overflow of the per-halo cache)
+	DevBuf pair_cache;              // 4 (tag,count) ways per catalogue-0 halo
 	DevBuf scratch[64];             // select pipeline temporaries
 	DevBuf scan_tmp;                // block sums of the scan primitive
 	DevBuf counters;                // small device counters (u64[64])

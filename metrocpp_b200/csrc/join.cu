@@ -109,39 +109,84 @@ __device__ __forceinline__ bool pair_add(PairEntry *tab, int log_cap, u64 hk)
 	return false;
 }
 
-#define JN_THREADS 256
-// One thread per sorted key.  A catalogue-0 member scans forward through the rest of its pid run
-// and emits one hit per catalogue-1 member it meets (the run holds all 0-members first).
-__global__ void __launch_bounds__(JN_THREADS) join_count_kernel(const u64 *__restrict__ keys, u64 n, KeyLayout L,
-								PairEntry *tab, int log_cap, u64 *counters)
+// ---- per-halo direct cache ---------------------------------------------------------------------
+// Almost every hit of a halo A goes to one or two partner halos B, so 4 (tag, count) ways per A
+// (one 32-byte sector, H0 x 32 B: L2 resident) absorb nearly all hits; only the overflow goes to
+// the general hash table above, which lives in DRAM.  tag = (B << 2tb) | (tA << tb) | tB.
+struct __align__(8) CacheWay { u32 tag; u32 count; };      // count biased by -1 like PairEntry
+#define CACHE_WAYS 4
+#define CACHE_EMPTY 0xFFFFFFFFu
+
+__device__ __forceinline__ bool cache_add(CacheWay *c, u32 tag)
 {
-	const u64 i = (u64) blockIdx.x * JN_THREADS + threadIdx.x;
-	u32 hits = 0;
-	bool overflow = false;
-	if (i < n) {
-		const u64 k = keys[i];
-		if (key_snap(L, k) == 0) {
-			const u64 pid = key_pid(L, k);
-			const u64 a_part = ((u64) key_halo(L, k) << (L.halo_bits + 2 * L.type_bits)) |
-					   ((u64) key_type(L, k) << L.type_bits);
-			for (u64 j = i + 1; j < n; j++) {
-				const u64 k2 = keys[j];
-				if (key_pid(L, k2) != pid) break;
-				if (key_snap(L, k2) == 0) continue;
-				const u64 hk = a_part | ((u64) key_halo(L, k2) << (2 * L.type_bits)) | (u64) key_type(L, k2);
-				if (!pair_add(tab, log_cap, hk)) overflow = true;
-				hits++;
-			}
+#pragma unroll
+	for (int w = 0; w < CACHE_WAYS; w++) {
+		u32 cur = *reinterpret_cast<volatile u32 *>(&c[w].tag);
+		if (cur == CACHE_EMPTY) {
+			cur = atomicCAS(&c[w].tag, CACHE_EMPTY, tag);
+			if (cur == CACHE_EMPTY) cur = tag;
+		}
+		if (cur == tag) { atomicAdd(&c[w].count, 1u); return true; }
+	}
+	return false;
+}
+
+#define JN_THREADS 256
+#define JN_ITEMS 8
+#define JN_TILE (JN_THREADS * JN_ITEMS)
+#define JN_HALO 32
+// Segmented run-length join.  A block stages a tile of sorted keys (+ a look-ahead halo) in shared
+// memory with coalesced 16-byte loads; every catalogue-0 member then walks the rest of its pid run
+// (all 0-members of a run precede its 1-members) and counts one hit per 1-member.
+__global__ void __launch_bounds__(JN_THREADS) join_count_kernel(const u64 *__restrict__ keys, u64 n, KeyLayout L,
+								CacheWay *cache, int use_cache, PairEntry *tab, int log_cap,
+								u64 *counters)
+{
+	__shared__ __align__(16) u64 s[JN_TILE + JN_HALO];
+	const u64 base = (u64) blockIdx.x * JN_TILE;
+	const u64 avail = n - base < (u64) (JN_TILE + JN_HALO) ? n - base : (u64) (JN_TILE + JN_HALO);
+	// base is a multiple of 2048 keys => 16-byte aligned
+	const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(keys + base);
+	for (u32 j = threadIdx.x; j < (JN_TILE + JN_HALO) / 2; j += JN_THREADS) {
+		if ((u64) (2 * j + 1) < avail) {
+			const ulonglong2 v = __ldg(src + j);
+			s[2 * j] = v.x; s[2 * j + 1] = v.y;
+		} else if ((u64) (2 * j) < avail) {
+			s[2 * j] = keys[base + 2 * j];
 		}
 	}
-	// hit statistics: one atomic per warp
+	__syncthreads();
+	const u32 in_tile = avail < (u64) JN_TILE ? (u32) avail : (u32) JN_TILE;
+	u32 hits = 0;
+	bool overflow = false;
+	const int tsh = L.type_bits;
+#pragma unroll 2
+	for (int it = 0; it < JN_ITEMS; it++) {
+		const u32 j = it * JN_THREADS + threadIdx.x;
+		if (j >= in_tile) break;
+		const u64 k = s[j];
+		if (key_snap(L, k) != 0) continue;
+		const u64 pid = key_pid(L, k);
+		const u32 A = key_halo(L, k), tA = key_type(L, k);
+		for (u64 t = j + 1; base + t < n; t++) {
+			const u64 k2 = t < (u64) (JN_TILE + JN_HALO) ? s[t] : keys[base + t];
+			if (key_pid(L, k2) != pid) break;
+			if (key_snap(L, k2) == 0) continue;
+			const u32 B = key_halo(L, k2), tB = key_type(L, k2);
+			hits++;
+			if (use_cache && cache_add(cache + (size_t) A * CACHE_WAYS, (B << (2 * tsh)) | (tA << tsh) | tB)) continue;
+			const u64 hk = ((u64) A << (L.halo_bits + 2 * tsh)) | ((u64) B << (2 * tsh)) | ((u64) tA << tsh) | (u64) tB;
+			if (!pair_add(tab, log_cap, hk)) overflow = true;
+		}
+	}
 #pragma unroll
 	for (int off = 16; off > 0; off >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, off);
 	if ((threadIdx.x & 31) == 0 && hits) atomicAdd((unsigned long long *) &counters[0], (unsigned long long) hits);
 	if (overflow) counters[1] = 1;
 }
 
-__global__ void table_compact_kernel(const PairEntry *__restrict__ tab, u64 cap, u64 *__restrict__ rec_key,
+// live entries of the hash table (mode 0: count into counters[3]; mode 1: append records)
+__global__ void table_compact_kernel(const PairEntry *__restrict__ tab, u64 cap, int mode, u64 *__restrict__ rec_key,
 				     u32 *__restrict__ rec_cnt, u64 *counters)
 {
 	const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,47 +197,73 @@ __global__ void table_compact_kernel(const PairEntry *__restrict__ tab, u64 cap,
 	const u32 ballot = __ballot_sync(0xffffffffu, live);
 	if (ballot == 0) return;
 	const int lane = threadIdx.x & 31;
-	u64 base = 0;
-	if (lane == 0) base = atomicAdd((unsigned long long *) &counters[2], (unsigned long long) __popc(ballot));
-	base = __shfl_sync(0xffffffffu, base, 0);
+	u64 b = 0;
+	if (lane == 0) b = atomicAdd((unsigned long long *) &counters[mode ? 2 : 3], (unsigned long long) __popc(ballot));
+	if (!mode) return;
+	b = __shfl_sync(0xffffffffu, b, 0);
 	if (live) {
-		const u64 dst = base + __popc(ballot & lanemask_lt());
+		const u64 dst = b + __popc(ballot & lanemask_lt());
 		rec_key[dst] = key;
 		rec_cnt[dst] = cnt;
 	}
 }
 
-__global__ void table_count_kernel(const PairEntry *__restrict__ tab, u64 cap, u64 *counters)
+// live ways of the direct cache, same two modes; rebuilds the 64-bit hit key
+__global__ void cache_compact_kernel(const CacheWay *__restrict__ cache, u64 n_ways, int mode, int halo_bits, int type_bits,
+				     u64 *__restrict__ rec_key, u32 *__restrict__ rec_cnt, u64 *counters)
 {
 	const u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x;
-	const bool live = i < cap && tab[i].key != PAIR_EMPTY;
+	u32 tag = CACHE_EMPTY, cnt = 0;
+	if (i < n_ways) { tag = cache[i].tag; cnt = cache[i].count + 1u; }
+	const bool live = tag != CACHE_EMPTY;
 	const u32 ballot = __ballot_sync(0xffffffffu, live);
-	if ((threadIdx.x & 31) == 0 && ballot) atomicAdd((unsigned long long *) &counters[3], (unsigned long long) __popc(ballot));
+	if (ballot == 0) return;
+	const int lane = threadIdx.x & 31;
+	u64 b = 0;
+	if (lane == 0) b = atomicAdd((unsigned long long *) &counters[mode ? 2 : 3], (unsigned long long) __popc(ballot));
+	if (!mode) return;
+	b = __shfl_sync(0xffffffffu, b, 0);
+	if (live) {
+		const u64 dst = b + __popc(ballot & lanemask_lt());
+		rec_key[dst] = ((i / CACHE_WAYS) << (halo_bits + 2 * type_bits)) | (u64) tag;
+		rec_cnt[dst] = cnt;
+	}
 }
 
 // scratch[0] = rec_key (u64[R]), scratch[1] = rec_cnt (u32[R])
 int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 n, i64 *n_records, i64 *n_hits)
 {
 	cudaStream_t st = ctx->stream;
-	const i64 H = ctx->cat[0].n_halos + ctx->cat[1].n_halos;
+	const i64 H0 = ctx->cat[0].n_halos;
+	const i64 H = H0 + ctx->cat[1].n_halos;
+	const int use_cache = (L.halo_bits + 2 * L.type_bits <= 31 && H0 > 0) ? 1 : 0;
+	const u64 n_ways = use_cache ? (u64) H0 * CACHE_WAYS : 0;
 	int log_cap = 16;
-	while ((1ll << log_cap) < 8 * H && log_cap < 40) log_cap++;
+	while ((1ll << log_cap) < (use_cache ? 2 : 8) * H && log_cap < 40) log_cap++;
 	u64 *counters = ctx->counters.as<u64>();
+	int rc;
+	if (use_cache && (rc = dev_reserve(ctx, ctx->pair_cache, n_ways * sizeof(CacheWay)))) return rc;
 	for (int attempt = 0;; attempt++) {
 		const u64 cap = 1ull << log_cap;
-		int rc = dev_reserve(ctx, ctx->table, cap * sizeof(PairEntry));
-		if (rc) return rc;
+		if ((rc = dev_reserve(ctx, ctx->table, cap * sizeof(PairEntry)))) return rc;
 		CUDA_TRY(ctx, cudaMemsetAsync(ctx->table.p, 0xFF, cap * sizeof(PairEntry), st));
+		if (use_cache) CUDA_TRY(ctx, cudaMemsetAsync(ctx->pair_cache.p, 0xFF, n_ways * sizeof(CacheWay), st));
 		CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 8 * sizeof(u64), st));
 		if (n > 0) {
-			join_count_kernel<<<(unsigned) div_up<i64>(n, JN_THREADS), JN_THREADS, 0, st>>>(sorted, (u64) n, L, ctx->table.as<PairEntry>(),
-													log_cap, counters);
+			join_count_kernel<<<(unsigned) div_up<i64>(n, JN_TILE), JN_THREADS, 0, st>>>(sorted, (u64) n, L, ctx->pair_cache.as<CacheWay>(), use_cache,
+												      ctx->table.as<PairEntry>(), log_cap, counters);
 			CUDA_TRY(ctx, cudaGetLastError());
 			ctx->launches++;
 		}
-		table_count_kernel<<<(unsigned) div_up<u64>(cap, 256), 256, 0, st>>>(ctx->table.as<PairEntry>(), cap, counters);
+		table_compact_kernel<<<(unsigned) div_up<u64>(cap, 256), 256, 0, st>>>(ctx->table.as<PairEntry>(), cap, 0, nullptr, nullptr, counters);
 		CUDA_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
+		if (use_cache) {
+			cache_compact_kernel<<<(unsigned) div_up<u64>(n_ways, 256), 256, 0, st>>>(ctx->pair_cache.as<CacheWay>(), n_ways, 0, L.halo_bits, L.type_bits,
+												   nullptr, nullptr, counters);
+			CUDA_TRY(ctx, cudaGetLastError());
+			ctx->launches++;
+		}
 		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
 		CUDA_TRY(ctx, cudaStreamSynchronize(st));
 		const bool overflow = ctx->h_counters[1] != 0;
@@ -200,17 +271,22 @@ int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 
 		if (!overflow) {
 			*n_hits = (i64) ctx->h_counters[0];
 			*n_records = (i64) live;
-			rc = dev_reserve(ctx, ctx->scratch[0], (size_t) (live + 1) * sizeof(u64));
-			if (rc) return rc;
-			rc = dev_reserve(ctx, ctx->scratch[1], (size_t) (live + 1) * sizeof(u32));
-			if (rc) return rc;
-			table_compact_kernel<<<(unsigned) div_up<u64>(cap, 256), 256, 0, st>>>(ctx->table.as<PairEntry>(), cap, ctx->scratch[0].as<u64>(),
+			if ((rc = dev_reserve(ctx, ctx->scratch[0], (size_t) (live + 1) * sizeof(u64)))) return rc;
+			if ((rc = dev_reserve(ctx, ctx->scratch[1], (size_t) (live + 1) * sizeof(u32)))) return rc;
+			table_compact_kernel<<<(unsigned) div_up<u64>(cap, 256), 256, 0, st>>>(ctx->table.as<PairEntry>(), cap, 1, ctx->scratch[0].as<u64>(),
 											       ctx->scratch[1].as<u32>(), counters);
 			CUDA_TRY(ctx, cudaGetLastError());
 			ctx->launches++;
+			if (use_cache) {
+				cache_compact_kernel<<<(unsigned) div_up<u64>(n_ways, 256), 256, 0, st>>>(ctx->pair_cache.as<CacheWay>(), n_ways, 1, L.halo_bits,
+													   L.type_bits, ctx->scratch[0].as<u64>(),
+													   ctx->scratch[1].as<u32>(), counters);
+				CUDA_TRY(ctx, cudaGetLastError());
+				ctx->launches++;
+			}
 			return METRO_OK;
 		}
-		if (attempt >= 6 || log_cap >= 38) {
+		if (attempt >= 8 || log_cap >= 38) {
 			metro_set_error(ctx, "pair table overflow at 2^%d entries", log_cap);
 			return METRO_ERR_UNSUPPORTED;
 		}
