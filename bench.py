@@ -386,7 +386,7 @@ def run_ours(args, rank, world, local_rank):
                        "sort_passes": info["sort_passes"], "l2": "inputs (>= 8 GB of keys per pass) far exceed the 126 MB L2",
                        "params": "minPartCmp=10 minPartHalo=100 facOrphanSteps=100 maxOrphanSteps=15 (fullbox cfg)",
                        "n_hits": info["n_hits"], "n_pairs": info["n_pairs"], "n_trees": info["n_trees"],
-                       "n_tokens": info["n_tokens"]},
+                       "n_tokens": info["n_tokens"], "n_table_hits": info["n_table_hits"]},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e

@@ -78,6 +78,7 @@ typedef struct {
 	int64_t n_pairs;                /* distinct (A,B) halo pairs with >= 1 shared tuple      */
 	int64_t n_tuples[2];
 	int32_t pid_bits, halo_bits, type_bits, sort_passes;
+	int64_t n_table_hits;           /* hits that missed the per-halo counter ways (hash-table path) */
 } metro_result_info;
 
 /* Host destination arrays for metro_result_fetch(); any pointer may be NULL (skipped).

@@ -31,7 +31,7 @@ class ResultInfo(C.Structure):
                 ("clean_count", C.c_int64), ("n_tokens", C.c_int64), ("n_untracked", C.c_int64),
                 ("n_hits", C.c_int64), ("n_pairs", C.c_int64), ("n_tuples", C.c_int64 * 2),
                 ("pid_bits", C.c_int32), ("halo_bits", C.c_int32), ("type_bits", C.c_int32),
-                ("sort_passes", C.c_int32)]
+                ("sort_passes", C.c_int32), ("n_table_hits", C.c_int64)]
 
 
 class ResultArrays(C.Structure):

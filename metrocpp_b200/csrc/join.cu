@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(JN_THREADS) join_count_kernel(const u64 *__res
 	}
 	__syncthreads();
 	const u32 in_tile = avail < (u64) JN_TILE ? (u32) avail : (u32) JN_TILE;
-	u32 hits = 0;
+	u32 hits = 0, slow = 0;
 	bool overflow = false;
 	const int tsh = L.type_bits;
 #pragma unroll 2
@@ -176,12 +176,14 @@ __global__ void __launch_bounds__(JN_THREADS) join_count_kernel(const u64 *__res
 			hits++;
 			if (use_cache && cache_add(cache + (size_t) A * CACHE_WAYS, (B << (2 * tsh)) | (tA << tsh) | tB)) continue;
 			const u64 hk = ((u64) A << (L.halo_bits + 2 * tsh)) | ((u64) B << (2 * tsh)) | ((u64) tA << tsh) | (u64) tB;
+			slow++;
 			if (!pair_add(tab, log_cap, hk)) overflow = true;
 		}
 	}
 #pragma unroll
-	for (int off = 16; off > 0; off >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, off);
+	for (int off = 16; off > 0; off >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, off); slow += __shfl_xor_sync(0xffffffffu, slow, off); }
 	if ((threadIdx.x & 31) == 0 && hits) atomicAdd((unsigned long long *) &counters[0], (unsigned long long) hits);
+	if ((threadIdx.x & 31) == 0 && slow) atomicAdd((unsigned long long *) &counters[5], (unsigned long long) slow);
 	if (overflow) counters[1] = 1;
 }
 
@@ -270,6 +272,7 @@ int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 
 		const u64 live = ctx->h_counters[3];
 		if (!overflow) {
 			*n_hits = (i64) ctx->h_counters[0];
+			ctx->res.info.n_table_hits = (i64) ctx->h_counters[5];
 			*n_records = (i64) live;
 			if ((rc = dev_reserve(ctx, ctx->scratch[0], (size_t) (live + 1) * sizeof(u64)))) return rc;
 			if ((rc = dev_reserve(ctx, ctx->scratch[1], (size_t) (live + 1) * sizeof(u32)))) return rc;

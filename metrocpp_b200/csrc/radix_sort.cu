@@ -173,12 +173,27 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const u64 *__restr
 		if (lane == 31) s_warpsum[warp] = incl;
 	}
 	__syncthreads();
+	u32 binstart = 0;
 	if (tid < SORT_RADIX) {
 		u32 pre = 0;
 #pragma unroll
 		for (int w = 0; w < SORT_RADIX / 32; w++) pre += (w < warp) ? s_warpsum[w] : 0u;
-		const u32 binstart = pre + incl - total;
-		// decoupled look-back: sum the counts of the preceding tiles for this digit
+		binstart = pre + incl - total;
+		s_binstart[tid] = binstart;
+	}
+	__syncthreads();
+
+	// ---- reorder the tile in shared memory (needs only tile-local offsets) ...
+#pragma unroll
+	for (int i = 0; i < OS_ITEMS; i++) {
+		const u32 d = (u32) (key[i] >> shift) & dmask;
+		const u32 pos = s_binstart[d] + wh[d] + rank[i];
+		s_keys[pos] = key[i];
+		if (HAS_VALS) s_vals[pos] = val[i];
+	}
+	// ---- ... and only then wait for the predecessors: decoupled look-back, one digit per thread.
+	// The tile's own count was published before the reorder, so the tiles behind it are not held up.
+	if (tid < SORT_RADIX) {
 		u64 excl = 0;
 		if (tile > 0) {
 			i64 t = (i64) tile - 1;
@@ -193,18 +208,7 @@ __global__ void __launch_bounds__(OS_THREADS) onesweep_kernel(const u64 *__restr
 			LB *mine = lookback + (size_t) tile * SORT_RADIX + tid;
 			*reinterpret_cast<volatile LB *>(mine) = T::INC | (LB) (excl + total);
 		}
-		s_binstart[tid] = binstart;
 		s_dst[tid] = (i64) (goff[tid] + excl) - (i64) binstart;
-	}
-	__syncthreads();
-
-	// ---- reorder the tile in shared memory
-#pragma unroll
-	for (int i = 0; i < OS_ITEMS; i++) {
-		const u32 d = (u32) (key[i] >> shift) & dmask;
-		const u32 pos = s_binstart[d] + wh[d] + rank[i];
-		s_keys[pos] = key[i];
-		if (HAS_VALS) s_vals[pos] = val[i];
 	}
 	__syncthreads();
 
