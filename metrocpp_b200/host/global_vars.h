@@ -1,0 +1,46 @@
+// global_vars.h -- the process-wide state the reference keeps in globals (reference
+// src/global_vars.h:35-130), reduced to what the matching path and its I/O touch.  The particle
+// containers (locParts / locMapParts, std::map<pid, vector<Particle>>) are replaced by flat
+// structure-of-arrays tuples: that is what the device ingests.
+#ifndef METRO_HOST_GLOBAL_VARS_H
+#define METRO_HOST_GLOBAL_VARS_H
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/metro_b200.h"
+#include "Halo.h"
+#include "MergerTree.h"
+
+struct TupleSoA {                      // one catalogue's "lines of the _particles files"
+	std::vector<uint64_t> pid;
+	std::vector<uint32_t> halo;    // index into locHalos[i]
+	std::vector<uint8_t> type;
+	void clear() { pid.clear(); halo.clear(); type.clear(); pid.shrink_to_fit(); halo.shrink_to_fit(); type.shrink_to_fit(); }
+};
+
+extern int locTask, totTask;
+extern std::vector<std::vector<Halo>> locHalos;             // [2][nHalos]
+extern std::vector<TupleSoA> locTuples;                     // [2]
+extern std::vector<std::vector<MergerTree>> locMTrees;      // [2]
+extern std::vector<std::vector<MergerTree>> locCleanTrees;  // [step]
+extern std::vector<uint64_t> allOrphIDs;
+extern int nLocHalos[2];
+extern int nPTypes;
+extern bool noPType;                                        // -DNOPTYPE behaviour: every type = 1
+extern int treeFlavour;                                     // METRO_FLAVOUR_*
+extern int minPartCmp, minPartHalo, facOrphanSteps, maxOrphanSteps;
+extern int nSnapsUse, nSnaps, nChunks, nGrid, nTreeChunks;
+extern int iNumCat, iUseCat;
+extern float boxSize;
+extern std::string cosmologicalModel;
+extern metro_ctx *gpuCtx;                                   // the engine context (one per process)
+extern bool keepRawTrees;                                   // fill locMTrees[] after FindProgenitors (off: only clean trees)
+extern bool slotDirty[2];                                   // host catalogue changed since last upload
+
+void InitLocVariables(bool needGpu = true);
+void CleanMemory(int iCat);
+metro_params CurrentParams();
+[[noreturn]] void Fatal(const std::string &msg);            // prints and exits non-zero
+
+#endif
