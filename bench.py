@@ -308,6 +308,10 @@ def run_ours(args, rank, world, local_rank):
     eng = mb.MetroEngine(local_rank)
     stream = torch.cuda.current_stream(dev)
     eng.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = [eng.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, device=dev)
+        eng.comm_init(rank, world, uid[0])
     eng.synth_pair_device(prm, spec)
     if world > 1:
         # catalogue npart of the earlier halos = sum over the pid shards
@@ -334,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pass_ms, stage = [], {"pack_hist": 0.0, "sort": 0.0, "join": 0.0, "select": 0.0}
+    pass_ms, stage = [], {"pack_hist": 0.0, "sort": 0.0, "join": 0.0, "exchange": 0.0, "select": 0.0}
     launches = 0
     ev0.record(stream)
     for _ in range(args.steps):
@@ -386,7 +390,11 @@ def run_ours(args, rank, world, local_rank):
                        "sort_passes": info["sort_passes"], "l2": "inputs (>= 8 GB of keys per pass) far exceed the 126 MB L2",
                        "params": "minPartCmp=10 minPartHalo=100 facOrphanSteps=100 maxOrphanSteps=15 (fullbox cfg)",
                        "n_hits": info["n_hits"], "n_pairs": info["n_pairs"], "n_trees": info["n_trees"],
-                       "n_tokens": info["n_tokens"], "n_table_hits": info["n_table_hits"]},
+                       "n_tokens": info["n_tokens"], "n_table_hits": info["n_table_hits"],
+                       "exchange_bytes_rank0": info["exchange_bytes"],
+                       "exchange": ("none (single GPU)" if world == 1 else
+                                    "partial pair counts -> owner(haloA)/owner(haloB): one grouped ncclSend/ncclRecv all-to-all "
+                                    "+ all-reduce(max) of bestDescendant and token flags")},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e

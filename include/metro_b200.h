@@ -79,6 +79,8 @@ typedef struct {
 	int64_t n_tuples[2];
 	int32_t pid_bits, halo_bits, type_bits, sort_passes;
 	int64_t n_table_hits;           /* hits that missed the per-halo counter ways (hash-table path) */
+	int64_t exchange_bytes;         /* multi-GPU: bytes this rank sent to its peers in the all-to-all */
+	int64_t owned_lo, owned_hi;     /* catalogue-0 halo range whose clean trees this rank holds */
 } metro_result_info;
 
 /* Host destination arrays for metro_result_fetch(); any pointer may be NULL (skipped).
@@ -101,7 +103,7 @@ typedef struct {
 
 /* Device timings (CUDA events on the context's stream) of the last metro_match_pair(), ms. */
 typedef struct {
-	float total, pack_hist, sort, join, select;
+	float total, pack_hist, sort, join, select, exchange;
 	int32_t sort_launches, total_launches;
 	float sort_pass_ms[8];
 } metro_timings;
@@ -148,6 +150,19 @@ int metro_catalogue_fetch_tuples(metro_ctx *ctx, int slot, uint64_t *pid, uint32
  * tuples of a catalogue are sharded over several GPUs by particle-ID range: the catalogue npart
  * entering the merit is the halo's GLOBAL size, which only the caller can sum over the shards. */
 int metro_catalogue_set_npart(metro_ctx *ctx, int slot, const int32_t *npart);
+
+/* ---- multi-GPU: one context per rank / GPU, NCCL over NVLink ---------------------------------
+ * Replaces the MPI layer of the path (src/Communication.cpp, src/Grid.cpp).  The caller shards the
+ * TUPLES of both catalogues by particle-ID range (any partition that keeps all memberships of a
+ * particle ID on one rank) and uploads the FULL halo tables on every rank.  metro_match_pair then
+ * joins locally, sends every partial (A,B,types,count) record to the ranks owning haloA / haloB
+ * (contiguous halo-index ranges) with one grouped all-to-all, and all-reduces the best-descendant
+ * and token arrays.  Each rank's result covers the clean trees of ITS range of catalogue-0 halos
+ * (concatenate in rank order); token_halo, n_tokens are global.  metro_shift appends the token
+ * tuples found in the rank's own shard.
+ * rank 0 calls metro_comm_unique_id, ships the 128 bytes to the others, all call metro_comm_init. */
+int metro_comm_unique_id(void *out128);
+int metro_comm_init(metro_ctx *ctx, int rank, int world, const void *unique_id128);
 
 /* ---- building blocks exposed for tests / benchmarks ------------------------------------ */
 /* LSD radix sort of n u64 keys (optionally with u32 values) on bits [begin_bit, end_bit);

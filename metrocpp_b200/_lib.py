@@ -31,7 +31,8 @@ class ResultInfo(C.Structure):
                 ("clean_count", C.c_int64), ("n_tokens", C.c_int64), ("n_untracked", C.c_int64),
                 ("n_hits", C.c_int64), ("n_pairs", C.c_int64), ("n_tuples", C.c_int64 * 2),
                 ("pid_bits", C.c_int32), ("halo_bits", C.c_int32), ("type_bits", C.c_int32),
-                ("sort_passes", C.c_int32), ("n_table_hits", C.c_int64)]
+                ("sort_passes", C.c_int32), ("n_table_hits", C.c_int64), ("exchange_bytes", C.c_int64),
+                ("owned_lo", C.c_int64), ("owned_hi", C.c_int64)]
 
 
 class ResultArrays(C.Structure):
@@ -43,7 +44,7 @@ class ResultArrays(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("total", C.c_float), ("pack_hist", C.c_float), ("sort", C.c_float), ("join", C.c_float),
-                ("select", C.c_float), ("sort_launches", C.c_int32), ("total_launches", C.c_int32),
+                ("select", C.c_float), ("exchange", C.c_float), ("sort_launches", C.c_int32), ("total_launches", C.c_int32),
                 ("sort_pass_ms", C.c_float * 8)]
 
 
@@ -70,6 +71,8 @@ SYMBOLS = {
     "metro_catalogue_fetch_halos": (C.c_int, [_P, C.c_int, _P, _P, _P, _P]),
     "metro_catalogue_fetch_tuples": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "metro_catalogue_set_npart": (C.c_int, [_P, C.c_int, _P]),
+    "metro_comm_unique_id": (C.c_int, [_P]),
+    "metro_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "metro_sort_u64": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int]),
     "metro_merit_bits": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P]),
     "metro_synth_pair_device": (C.c_int, [_P, C.POINTER(Params), C.POINTER(SynthSpec)]),

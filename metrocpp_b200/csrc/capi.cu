@@ -97,6 +97,7 @@ void metro_ctx_destroy(metro_ctx *ctx)
 	for (int d = 0; d < 2; d++) { dev_free(r.raw_off[d]); dev_free(r.raw_prog[d]); dev_free(r.raw_ncommon[d]); dev_free(r.raw_merit[d]); }
 	dev_free(r.tree_main); dev_free(r.tree_orphan); dev_free(r.tree_off); dev_free(r.clean_prog); dev_free(r.clean_ncommon); dev_free(r.token_halo);
 	sort_workspace_free(ctx->sortws);
+	comm_destroy(ctx);
 	dev_free(ctx->keys_a); dev_free(ctx->keys_b); dev_free(ctx->table); dev_free(ctx->pair_cache); dev_free(ctx->scan_tmp); dev_free(ctx->counters);
 	for (DevBuf &b : ctx->scratch) dev_free(b);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
@@ -263,7 +264,27 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	if ((rc = stage_join_count(ctx, L, sorted, N, &R, &hits))) return rc;
 	res.info.n_hits = hits;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
-	if ((rc = stage_select(ctx, prm, L, R))) return rc;
+	// multi-GPU: partial pair counts -> owner(haloA) / owner(haloB) (no-op on one GPU)
+	const u64 *rak, *rbk; const u32 *rac, *rbc;
+	i64 RA = 0, RB = 0, a_lo = 0, a_hi = 0;
+	ctx->exchange_bytes = 0;
+	if ((rc = comm_exchange_records(ctx, halo_bits, type_bits, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), R, &rak, &rac, &RA, &rbk,
+					&rbc, &RB))) return rc;
+	comm_owned_range(ctx, c0.n_halos, &a_lo, &a_hi);
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[7], st));
+	if ((rc = stage_select(ctx, prm, L, rak, rac, RA, rbk, rbc, RB, a_lo, a_hi))) return rc;
+	res.info.exchange_bytes = ctx->exchange_bytes;
+	res.info.owned_lo = a_lo; res.info.owned_hi = a_hi;
+	if (ctx->world > 1) {
+		// global statistics for the caller
+		u64 *d = ctx->counters.as<u64>() + 56;
+		u64 h[3] = {(u64) res.info.n_hits, (u64) res.info.n_untracked, (u64) res.info.n_table_hits};
+		CUDA_TRY(ctx, cudaMemcpyAsync(d, h, sizeof h, cudaMemcpyHostToDevice, st));
+		if ((rc = comm_allreduce_sum_u64(ctx, d, 3))) return rc;
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 56, d, sizeof h, cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		res.info.n_hits = (i64) ctx->h_counters[56]; res.info.n_untracked = (i64) ctx->h_counters[57]; res.info.n_table_hits = (i64) ctx->h_counters[58];
+	}
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[4], st));
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	metro_timings &tm = ctx->timings;
@@ -271,7 +292,8 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	cudaEventElapsedTime(&tm.pack_hist, ctx->ev[0], ctx->ev[1]);
 	cudaEventElapsedTime(&tm.sort, ctx->ev[1], ctx->ev[2]);
 	cudaEventElapsedTime(&tm.join, ctx->ev[2], ctx->ev[3]);
-	cudaEventElapsedTime(&tm.select, ctx->ev[3], ctx->ev[4]);
+	cudaEventElapsedTime(&tm.exchange, ctx->ev[3], ctx->ev[7]);
+	cudaEventElapsedTime(&tm.select, ctx->ev[7], ctx->ev[4]);
 	if (N > 0) for (int p = 0; p < plan.n_pass; p++) cudaEventElapsedTime(&tm.sort_pass_ms[p], ctx->ev_pass[p], ctx->ev_pass[p + 1]);
 	tm.sort_launches = N > 0 ? plan.n_pass : 0;
 	tm.total_launches = ctx->launches;

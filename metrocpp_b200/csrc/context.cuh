@@ -4,6 +4,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/metro_b200.h"
 #include "common.cuh"
 #include "radix_sort.cuh"
@@ -59,7 +61,7 @@ struct metro_ctx {
 	DevBuf keys_a, keys_b;          // packed join keys, ping-pong
 	DevBuf table;                   // pair-count hash table (overflow of the per-halo cache)
 	DevBuf pair_cache;              // 4 (tag,count) ways per catalogue-0 halo
-	DevBuf scratch[64];             // select pipeline temporaries
+	DevBuf scratch[80];             // select pipeline temporaries
 	DevBuf scan_tmp;                // block sums of the scan primitive
 	DevBuf counters;                // small device counters (u64[64])
 	u64 *h_counters = nullptr;      // pinned mirror
@@ -67,6 +69,11 @@ struct metro_ctx {
 	cudaEvent_t ev_pass[SORT_MAX_PASSES + 1];
 	metro_timings timings;
 	int launches = 0;
+	// multi-GPU (one context per rank); comm is an ncclComm_t
+	int rank = 0, world = 1;
+	void *comm = nullptr;
+	i64 exchange_bytes = 0;         // bytes this rank sent to peers in the last all-to-all
+	DevBuf xsend_key, xsend_cnt, xrecvA_key, xrecvA_cnt, xrecvB_key, xrecvB_cnt, xcounts;
 };
 
 int dev_reserve(metro_ctx *ctx, DevBuf &b, size_t bytes);
@@ -80,7 +87,15 @@ int scan_exclusive_u32(metro_ctx *ctx, cudaStream_t st, const u32 *in, u32 *out,
 int stage_pack_hist(metro_ctx *ctx, const KeyLayout &L, const SortPlan &plan);      // join.cu
 int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 n,
 		     i64 *n_records, i64 *n_hits);                                     // join.cu
-int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &L, i64 n_records);   // select.cu
+int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &L, const u64 *recA_key, const u32 *recA_cnt, i64 RA,
+		 const u64 *recB_key, const u32 *recB_cnt, i64 RB, i64 a_lo, i64 a_hi);           // select.cu
+// comm.cu (NCCL; no-ops on a single GPU)
+int comm_allreduce_max_i32(metro_ctx *ctx, i32 *buf, i64 n);
+int comm_allreduce_sum_u64(metro_ctx *ctx, u64 *buf, i64 n);
+int comm_exchange_records(metro_ctx *ctx, int halo_bits, int type_bits, const u64 *rec_key, const u32 *rec_cnt, i64 R,
+			  const u64 **recA_key, const u32 **recA_cnt, i64 *RA, const u64 **recB_key, const u32 **recB_cnt, i64 *RB);
+void comm_owned_range(const metro_ctx *ctx, i64 H, i64 *lo, i64 *hi);
+void comm_destroy(metro_ctx *ctx);
 int stage_shift(metro_ctx *ctx, const metro_params *prm);                            // shift.cu
 int merit_bits_device(metro_ctx *ctx, i64 n, const i32 *a, const i32 *b, const i32 *c, const i32 *d, u32 *out);   // select.cu
 int catalogue_scan_tuples(metro_ctx *ctx, DevCatalogue &c, int nptypes);             // shift.cu: max pid + validation

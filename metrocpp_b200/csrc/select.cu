@@ -208,13 +208,13 @@ __global__ void clean_flag_kernel(const u32 *raw_main0, const i32 *raw_prog0, i6
 }
 
 // orphan / token rule (CleanTrees :575-617)
-__global__ void orphan_kernel(const u32 *cntc, const i32 *nptot0, const i32 *norph0, i64 H0, i32 min_part_halo, i32 fac, i32 maxs,
-			      u32 *token, u32 *nfin, u32 *has_tree, u64 *counters)
+__global__ void orphan_kernel(const u32 *cntc, const i32 *nptot0, const i32 *norph0, i64 H0, i64 a_lo, i64 a_hi, i32 min_part_halo, i32 fac,
+			      i32 maxs, u32 *token, u32 *nfin, u32 *has_tree, u64 *counters)
 {
 	TID;
 	if (i >= H0) return;
 	u32 tk = 0;
-	if (cntc[i] == 0 && nptot0[i] > min_part_halo) {
+	if (i >= a_lo && i < a_hi && cntc[i] == 0 && nptot0[i] > min_part_halo) {
 		const i32 steps = norph0[i] + 1;
 		i32 loc = 1 + nptot0[i] / fac;
 		if (loc > maxs) loc = maxs;
@@ -341,30 +341,22 @@ static int build_tree(metro_ctx *ctx, const DirList &L, i64 H_main, int T, const
 	return METRO_OK;
 }
 
-int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, i64 R)
+// Records (hit key, count) -> distinct (A,B) pairs with per-type counts for both directions,
+// thresholded (AssignMap) and compacted in (A, ID(B)) order.  Outputs in O[0..4]:
+// kA u32[K], kB u32[K], kF i32[K*T] (counts by typeB), kK i32[K*T] (by typeA), ktot i32[K].
+static int merge_records(metro_ctx *ctx, const metro_params *prm, HitLayout hl, int hbits, const u64 *rec_key, const u32 *rec_cnt, i64 R,
+			 const u32 *rank1, DevBuf *O, i64 *K_out, i64 *P_out)
 {
 	cudaStream_t st = ctx->stream;
 	const int T = prm->nptypes;
-	DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
-	const i64 H0 = c0.n_halos, H1 = c1.n_halos;
-	DevBuf *S = ctx->scratch;        // [0]=rec_key [1]=rec_cnt (from stage_join_count)
-	DevResult &res = ctx->res;
+	DevBuf *S = ctx->scratch;
 	u64 *cnt = ctx->counters.as<u64>();
-	HitLayout hl = {KL.halo_bits, KL.type_bits};
-	const int hbits = KL.halo_bits;
 	u64 tot = 0;
-
-	// halo-ID ranks (std::map iteration order of indexCommon is ascending halo ID, not file order)
-	TRY(id_ranks(ctx, c0, S[2], S + 40));
-	TRY(id_ranks(ctx, c1, S[3], S + 40));
-	const u32 *rank0 = S[2].as<u32>(), *rank1 = S[3].as<u32>();
-
-	// 1. order the records by (A, ID(B)) and merge the per-type records of each pair
 	i64 P = 0;
 	RES(S[4], R * 8); RES(S[5], R * 8); RES(S[6], R * 4); RES(S[7], R * 4); RES(S[8], R * 4); RES(S[9], R * 4);
 	u32 *order = nullptr;
 	if (R > 0) {
-		rec_key_kernel<<<GRID(R), TPB, 0, st>>>(S[0].as<u64>(), R, hl, rank1, S[4].as<u64>(), S[6].as<u32>()); LAUNCHED();
+		rec_key_kernel<<<GRID(R), TPB, 0, st>>>(rec_key, R, hl, rank1, S[4].as<u64>(), S[6].as<u32>()); LAUNCHED();
 		u64 *rk;
 		TRY(sort_kv(ctx, S[4].as<u64>(), S[5].as<u64>(), S[6].as<u32>(), S[7].as<u32>(), R, 32 + hbits, &rk, &order));
 		head_flag_kernel<<<GRID(R), TPB, 0, st>>>(rk, R, S[8].as<u32>()); LAUNCHED();
@@ -372,30 +364,62 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, i
 		TRY(read_total(ctx, cnt + 5, &tot));
 		P = (i64) tot;
 	}
-	res.info.n_pairs = P;
 	RES(S[10], P * 4); RES(S[11], P * 4); RES(S[12], P * T * 4); RES(S[13], P * T * 4); RES(S[14], P * 4);
 	i64 K = 0;
 	if (P > 0) {
 		CUDA_TRY(ctx, cudaMemsetAsync(S[12].p, 0, (size_t) P * T * 4, st));
 		CUDA_TRY(ctx, cudaMemsetAsync(S[13].p, 0, (size_t) P * T * 4, st));
 		CUDA_TRY(ctx, cudaMemsetAsync(S[14].p, 0, (size_t) P * 4, st));
-		pair_merge_kernel<<<GRID(R), TPB, 0, st>>>(S[0].as<u64>(), S[1].as<u32>(), order, S[8].as<u32>(), S[9].as<u32>(), R, hl, T,
+		pair_merge_kernel<<<GRID(R), TPB, 0, st>>>(rec_key, rec_cnt, order, S[8].as<u32>(), S[9].as<u32>(), R, hl, T,
 							    S[10].as<u32>(), S[11].as<u32>(), S[12].as<i32>(), S[13].as<i32>(), S[14].as<i32>());
 		LAUNCHED();
-		// 2. AssignMap threshold, ordered compaction
+		// AssignMap threshold, ordered compaction
 		RES(S[15], P * 4); RES(S[16], P * 4);
 		keep_flag_kernel<<<GRID(P), TPB, 0, st>>>(S[14].as<i32>(), P, prm->min_part_cmp, S[15].as<u32>()); LAUNCHED();
 		TRY(scan_exclusive_u32(ctx, st, S[15].as<u32>(), S[16].as<u32>(), P, cnt + 5));
 		TRY(read_total(ctx, cnt + 5, &tot));
 		K = (i64) tot;
 	}
-	// kept pairs in forward order: kA S[17], kB S[18], kF S[19], kK S[20], ktot S[21]
-	RES(S[17], K * 4); RES(S[18], K * 4); RES(S[19], K * T * 4); RES(S[20], K * T * 4); RES(S[21], K * 4);
+	RES(O[0], K * 4); RES(O[1], K * 4); RES(O[2], K * T * 4); RES(O[3], K * T * 4); RES(O[4], K * 4);
 	if (K > 0) {
 		pair_compact_kernel<<<GRID(P), TPB, 0, st>>>(S[15].as<u32>(), S[16].as<u32>(), P, T, S[10].as<u32>(), S[11].as<u32>(), S[12].as<i32>(),
-							      S[13].as<i32>(), S[14].as<i32>(), S[17].as<u32>(), S[18].as<u32>(), S[19].as<i32>(),
-							      S[20].as<i32>(), S[21].as<i32>());
+							      S[13].as<i32>(), S[14].as<i32>(), O[0].as<u32>(), O[1].as<u32>(), O[2].as<i32>(),
+							      O[3].as<i32>(), O[4].as<i32>());
 		LAUNCHED();
+	}
+	*K_out = K; *P_out = P;
+	return METRO_OK;
+}
+
+// recA: records whose haloA this rank owns (forward trees); recB: records whose haloB it owns
+// (backward trees).  On one GPU both are the same array.  [a_lo, a_hi) = owned catalogue-0 halos.
+int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, const u64 *recA_key, const u32 *recA_cnt, i64 RA,
+		 const u64 *recB_key, const u32 *recB_cnt, i64 RB, i64 a_lo, i64 a_hi)
+{
+	cudaStream_t st = ctx->stream;
+	const int T = prm->nptypes;
+	DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
+	const i64 H0 = c0.n_halos, H1 = c1.n_halos;
+	DevBuf *S = ctx->scratch;
+	DevResult &res = ctx->res;
+	u64 *cnt = ctx->counters.as<u64>();
+	HitLayout hl = {KL.halo_bits, KL.type_bits};
+	const int hbits = KL.halo_bits;
+
+	// halo-ID ranks (std::map iteration order of indexCommon is ascending halo ID, not file order)
+	TRY(id_ranks(ctx, c0, S[2], S + 40));
+	TRY(id_ranks(ctx, c1, S[3], S + 40));
+	const u32 *rank0 = S[2].as<u32>(), *rank1 = S[3].as<u32>();
+
+	// 1.-2. distinct pairs above the threshold: forward set -> S[17..21], backward set -> S[64..68]
+	i64 K = 0, P = 0, KB = 0, PB = 0;
+	TRY(merge_records(ctx, prm, hl, hbits, recA_key, recA_cnt, RA, rank1, S + 17, &K, &P));
+	res.info.n_pairs = P;
+	DevBuf *B = S + 17;
+	KB = K;
+	if (recB_key != recA_key) {
+		TRY(merge_records(ctx, prm, hl, hbits, recB_key, recB_cnt, RB, rank1, S + 64, &KB, &PB));
+		B = S + 64;
 	}
 
 	// 3. forward raw tree (locMTrees[0])
@@ -403,30 +427,32 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, i
 	TRY(build_tree(ctx, fwd, H0, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), hbits, S + 40, S[22], S[23], S[24], res.raw_prog[0],
 		       res.raw_ncommon[0], res.raw_merit[0]));
 	// 4. backward raw tree (locMTrees[1]): same pairs ordered by (B, ID(A)), by-type counts of the 0 side
-	RES(S[25], K * 4); RES(S[26], K * 4); RES(S[27], K * T * 4); RES(S[28], K * 4);
-	if (K > 0) {
-		RES(S[40], K * 8); RES(S[41], K * 8); RES(S[42], K * 4); RES(S[43], K * 4);
-		bwd_key_kernel<<<GRID(K), TPB, 0, st>>>(S[17].as<u32>(), S[18].as<u32>(), rank0, K, S[40].as<u64>(), S[42].as<u32>()); LAUNCHED();
+	RES(S[25], KB * 4); RES(S[26], KB * 4); RES(S[27], KB * T * 4); RES(S[28], KB * 4);
+	if (KB > 0) {
+		RES(S[40], KB * 8); RES(S[41], KB * 8); RES(S[42], KB * 4); RES(S[43], KB * 4);
+		bwd_key_kernel<<<GRID(KB), TPB, 0, st>>>(B[0].as<u32>(), B[1].as<u32>(), rank0, KB, S[40].as<u64>(), S[42].as<u32>()); LAUNCHED();
 		u64 *rk; u32 *perm;
-		TRY(sort_kv(ctx, S[40].as<u64>(), S[41].as<u64>(), S[42].as<u32>(), S[43].as<u32>(), K, 32 + hbits, &rk, &perm));
-		gather_dir_kernel<<<GRID(K), TPB, 0, st>>>(perm, K, T, S[18].as<u32>(), S[17].as<u32>(), S[20].as<i32>(), S[21].as<i32>(),
-							    S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>());
+		TRY(sort_kv(ctx, S[40].as<u64>(), S[41].as<u64>(), S[42].as<u32>(), S[43].as<u32>(), KB, 32 + hbits, &rk, &perm));
+		gather_dir_kernel<<<GRID(KB), TPB, 0, st>>>(perm, KB, T, B[1].as<u32>(), B[0].as<u32>(), B[3].as<i32>(), B[4].as<i32>(),
+							     S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>());
 		LAUNCHED();
 	}
-	DirList bwd = {S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>(), K};
+	DirList bwd = {S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>(), KB};
 	TRY(build_tree(ctx, bwd, H1, T, c1.npart_tot.as<i32>(), c0.npart_tot.as<i32>(), hbits, S + 40, S[29], S[30], S[31], res.raw_prog[1],
 		       res.raw_ncommon[1], res.raw_merit[1]));
-	res.info.raw_count[0] = res.info.raw_count[1] = K;
+	res.info.raw_count[0] = K; res.info.raw_count[1] = KB;
 	for (int d = 0; d < 2; d++) {
 		const i64 H = d ? H1 : H0;
 		RES(res.raw_off[d], (H + 1) * 8);
-		off32_to_64_kernel<<<GRID(H + 1), TPB, 0, st>>>((d ? S[30] : S[23]).as<u32>(), H, (u64) K, res.raw_off[d].as<i64>());
+		off32_to_64_kernel<<<GRID(H + 1), TPB, 0, st>>>((d ? S[30] : S[23]).as<u32>(), H, (u64) (d ? KB : K), res.raw_off[d].as<i64>());
 		LAUNCHED();
 	}
 
 	// 5. CleanTrees: mutual-best filter
 	RES(S[32], (H1 + 1) * 4);
 	best_desc_kernel<<<GRID(H1), TPB, 0, st>>>(S[30].as<u32>(), S[29].as<u32>(), res.raw_prog[1].as<i32>(), H1, S[32].as<i32>()); LAUNCHED();
+	// multi-GPU: the owner of each catalogue-1 halo knows its best descendant, everybody needs it
+	TRY(comm_allreduce_max_i32(ctx, S[32].as<i32>(), H1));
 	RES(S[33], K * 4); RES(S[34], K * 4); RES(S[35], (H0 + 1) * 4); RES(S[36], (H0 + 1) * 4);
 	u32 *cntc = S[35].as<u32>(), *cstart = S[36].as<u32>();
 	CUDA_TRY(ctx, cudaMemsetAsync(cntc, 0, (size_t) (H0 + 1) * 4, st));
@@ -445,7 +471,7 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, i
 	CUDA_TRY(ctx, cudaMemsetAsync(nfin, 0, (size_t) (H0 + 1) * 4, st));
 	CUDA_TRY(ctx, cudaMemsetAsync(has_tree, 0, (size_t) (H0 + 1) * 4, st));
 	if (H0 > 0) {
-		orphan_kernel<<<GRID(H0), TPB, 0, st>>>(cntc, c0.npart_tot.as<i32>(), c0.n_orphan_steps.as<i32>(), H0, prm->min_part_halo,
+		orphan_kernel<<<GRID(H0), TPB, 0, st>>>(cntc, c0.npart_tot.as<i32>(), c0.n_orphan_steps.as<i32>(), H0, a_lo, a_hi, prm->min_part_halo,
 							 prm->fac_orphan_steps, prm->max_orphan_steps, token, nfin, has_tree, cnt);
 		LAUNCHED();
 	}
@@ -454,7 +480,12 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, i
 	u32 *coff = Q[0].as<u32>(), *tscan = Q[1].as<u32>(), *kscan = Q[2].as<u32>();
 	TRY(scan_exclusive_u32(ctx, st, nfin, coff, H0 + 1, cnt + 5));
 	TRY(scan_exclusive_u32(ctx, st, has_tree, tscan, H0 + 1, cnt + 6));
-	TRY(scan_exclusive_u32(ctx, st, token, kscan, H0 + 1, cnt + 7));
+	// the token list is global (every rank appends all token halos in the shift): OR the per-rank flags
+	RES(Q[11], (H0 + 1) * 4);
+	u32 *gtoken = Q[11].as<u32>();
+	CUDA_TRY(ctx, cudaMemcpyAsync(gtoken, token, (size_t) (H0 + 1) * 4, cudaMemcpyDeviceToDevice, st));
+	TRY(comm_allreduce_max_i32(ctx, reinterpret_cast<i32 *>(gtoken), H0));
+	TRY(scan_exclusive_u32(ctx, st, gtoken, kscan, H0 + 1, cnt + 7));
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, cnt, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	const i64 C = (i64) ctx->h_counters[5], NT = (i64) ctx->h_counters[6], NK = (i64) ctx->h_counters[7];
@@ -483,7 +514,7 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, i
 		tree_emit_kernel<<<GRID(H0), TPB, 0, st>>>(has_tree, tscan, token, coff, H0, res.tree_main.as<i32>(), res.tree_orphan.as<u8>(),
 							    res.tree_off.as<i64>());
 		LAUNCHED();
-		token_emit_kernel<<<GRID(H0), TPB, 0, st>>>(token, kscan, H0, res.token_halo.as<i32>()); LAUNCHED();
+		token_emit_kernel<<<GRID(H0), TPB, 0, st>>>(gtoken, kscan, H0, res.token_halo.as<i32>()); LAUNCHED();
 	}
 	set_i64_kernel<<<1, 1, 0, st>>>(res.tree_off.as<i64>() + NT, C); LAUNCHED();
 	return METRO_OK;

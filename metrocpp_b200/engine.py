@@ -184,13 +184,22 @@ class MetroEngine:
     def timings(self) -> dict:
         t = _lib.Timings()
         self._check(self.lib.metro_get_timings(self.h, C.byref(t)))
-        d = {k: getattr(t, k) for k in ("total", "pack_hist", "sort", "join", "select", "sort_launches", "total_launches")}
+        d = {k: getattr(t, k) for k in ("total", "pack_hist", "sort", "join", "select", "exchange", "sort_launches", "total_launches")}
         d["sort_pass_ms"] = list(t.sort_pass_ms)
         return d
 
     # -- ShiftHalosPartsGrids ------------------------------------------------------------------
     def shift_halos_parts(self, prm: Params):
         self._check(self.lib.metro_shift(self.h, C.byref(prm)))
+
+    # -- multi-GPU ---------------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.metro_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        self._check(self.lib.metro_comm_init(self.h, rank, world, C.c_char_p(unique_id)))
 
     # -- building blocks -------------------------------------------------------------------------
     def merit_bits(self, n_comm, n_ph0, n_ph1, i_m) -> np.ndarray:
