@@ -228,7 +228,14 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	const i64 N = c0.n_tuples + c1.n_tuples;
 	const i64 Hmax = std::max(c0.n_halos, c1.n_halos);
 	// key layout: pid | snap | halo | type must fit one u64 (see common.cuh)
-	int pid_bits = std::max(1, ceil_log2_u64(std::max(c0.max_pid, c1.max_pid)));
+	// particle IDs enter the key relative to the smallest one present (a pid-range shard of a
+	// multi-GPU run spans fewer bits than the global IDs => fewer sort passes)
+	u64 pid_base = ~0ull;
+	if (c0.n_tuples > 0) pid_base = std::min(pid_base, c0.min_pid);
+	if (c1.n_tuples > 0) pid_base = std::min(pid_base, c1.min_pid);
+	if (pid_base == ~0ull) pid_base = 0;
+	ctx->pid_base = pid_base;
+	int pid_bits = std::max(1, ceil_log2_u64(std::max(c0.max_pid, c1.max_pid) - pid_base));
 	int halo_bits = std::max(1, ceil_log2_u64(Hmax > 0 ? (u64) (Hmax - 1) : 0));
 	int type_bits = prm->nptypes > 1 ? ceil_log2_u64((u64) prm->nptypes - 1) : 0;
 	if (pid_bits + 1 + halo_bits + type_bits > 64 || 2 * halo_bits + 2 * type_bits > 63) {

@@ -77,19 +77,42 @@ __global__ void route_count_kernel(const u64 *__restrict__ rec, i64 n, int halo_
 	for (int i = threadIdx.x; i < 2 * world; i += blockDim.x) if (sh[i]) atomicAdd(&counts[i], (unsigned long long) sh[i]);
 }
 
-__global__ void route_scatter_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cnt, i64 n, int halo_bits, int type_bits, i64 chunk0,
-				     i64 chunk1, int world, unsigned long long *cursor /* [2*world], preset to the slot offsets */,
-				     u64 *__restrict__ out_key, u32 *__restrict__ out_cnt)
+// Block-aggregated scatter: a block counts its records per destination slot in shared memory,
+// reserves one contiguous run per slot with a single global atomic each, then places its records
+// (the order inside a slot is irrelevant: the owner sums the partials).
+__global__ void __launch_bounds__(256) route_scatter_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cnt, i64 n, int halo_bits,
+							    int type_bits, i64 chunk0, i64 chunk1, int world,
+							    unsigned long long *cursor /* [2*world], preset to the slot offsets */,
+							    u64 *__restrict__ out_key, u32 *__restrict__ out_cnt)
 {
+	extern __shared__ unsigned long long shb[];                  // [2*world] block bases, then u32 [2*world] counts
+	unsigned int *shc = reinterpret_cast<unsigned int *>(shb + 2 * world);
+	for (int i = threadIdx.x; i < 2 * world; i += blockDim.x) shc[i] = 0;
+	__syncthreads();
 	const u64 hm = (1ull << halo_bits) - 1ull;
-	for (i64 i = (i64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (i64) gridDim.x * blockDim.x) {
+	const i64 per = (n + gridDim.x - 1) / gridDim.x;
+	const i64 lo = (i64) blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+	for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		const u64 hk = rec[i];
+		const i64 B = (i64) ((hk >> (2 * type_bits)) & hm), A = (i64) ((hk >> (2 * type_bits + halo_bits)) & hm);
+		atomicAdd(&shc[(int) (A / chunk0)], 1u);
+		atomicAdd(&shc[world + (int) (B / chunk1)], 1u);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < 2 * world; i += blockDim.x) {
+		shb[i] = shc[i] ? atomicAdd(&cursor[i], (unsigned long long) shc[i]) : 0ull;
+		shc[i] = 0;
+	}
+	__syncthreads();
+	for (i64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
 		const u64 hk = rec[i];
 		const u32 c = cnt[i];
 		const i64 B = (i64) ((hk >> (2 * type_bits)) & hm), A = (i64) ((hk >> (2 * type_bits + halo_bits)) & hm);
-		const unsigned long long a = atomicAdd(&cursor[(int) (A / chunk0)], 1ull);
+		const int sa = (int) (A / chunk0), sb = world + (int) (B / chunk1);
+		const unsigned long long a = shb[sa] + atomicAdd(&shc[sa], 1u);
 		out_key[a] = hk; out_cnt[a] = c;
-		const unsigned long long b = atomicAdd(&cursor[world + (int) (B / chunk1)], 1ull);
-		out_key[b] = hk; out_cnt[b] = c;
+		const unsigned long long b2 = shb[sb] + atomicAdd(&shc[sb], 1u);
+		out_key[b2] = hk; out_cnt[b2] = c;
 	}
 }
 
@@ -138,7 +161,7 @@ int comm_exchange_records(metro_ctx *ctx, int halo_bits, int type_bits, const u6
 	if ((rc = dev_reserve(ctx, ctx->xrecvB_cnt, (size_t) (nB + 1) * 4))) return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_cursor, soff.data(), (size_t) 2 * W * sizeof(u64), cudaMemcpyHostToDevice, st));
 	if (R > 0) {
-		route_scatter_kernel<<<blocks, 256, 0, st>>>(rec_key, rec_cnt, R, halo_bits, type_bits, chunk0, chunk1, W, d_cursor,
+		route_scatter_kernel<<<blocks, 256, (size_t) 2 * W * 12, st>>>(rec_key, rec_cnt, R, halo_bits, type_bits, chunk0, chunk1, W, d_cursor,
 							      ctx->xsend_key.as<u64>(), ctx->xsend_cnt.as<u32>());
 		CUDA_TRY(ctx, cudaGetLastError());
 		ctx->launches++;

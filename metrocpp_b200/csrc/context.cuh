@@ -33,7 +33,7 @@ struct DevCatalogue {
 	const u64 *b_pid = nullptr;
 	const u32 *b_halo = nullptr;
 	const u8 *b_type = nullptr;
-	u64 max_pid = 0;
+	u64 max_pid = 0, min_pid = 0;
 	bool valid = false;
 	const u64 *d_pid() const { return b_pid ? b_pid : pid.as<u64>(); }
 	const u32 *d_halo() const { return b_pid ? b_halo : halo.as<u32>(); }
@@ -72,6 +72,7 @@ struct metro_ctx {
 	// multi-GPU (one context per rank); comm is an ncclComm_t
 	int rank = 0, world = 1;
 	void *comm = nullptr;
+	u64 pid_base = 0;               // subtracted from every pid when the join key is packed
 	i64 exchange_bytes = 0;         // bytes this rank sent to peers in the last all-to-all
 	DevBuf xsend_key, xsend_cnt, xrecvA_key, xrecvA_cnt, xrecvB_key, xrecvB_cnt, xcounts;
 };

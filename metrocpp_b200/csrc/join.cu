@@ -17,7 +17,7 @@
 // ---- pack + histogram ------------------------------------------------------------------------
 // 13 B read + 8 B written per tuple; the P digit histograms ride along (no extra pass).
 __global__ void __launch_bounds__(PK_THREADS) pack_hist_kernel(const u64 *__restrict__ pid, const u32 *__restrict__ halo,
-							       const u8 *__restrict__ type, u64 n, u32 snap,
+							       const u8 *__restrict__ type, u64 n, u32 snap, u64 pid_base,
 							       KeyLayout L, SortPlan plan, u64 *__restrict__ keys,
 							       u64 *__restrict__ ghist)
 {
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(PK_THREADS) pack_hist_kernel(const u64 *__rest
 		for (int k = 0; k < PK_ITEMS; k++) {
 			const u64 i = base + (u64) k * PK_THREADS + threadIdx.x;
 			if (i < n) {
-				const u64 key = key_pack(L, p[k], snap, h[k], t[k] & L.type_mask);
+				const u64 key = key_pack(L, p[k] - pid_base, snap, h[k], t[k] & L.type_mask);
 				st_stream_u64(keys + i, key);
 				hist_accumulate(sh, key, plan);
 			}
@@ -65,7 +65,7 @@ int stage_pack_hist(metro_ctx *ctx, const KeyLayout &L, const SortPlan &plan)
 		const DevCatalogue &c = ctx->cat[s];
 		if (c.n_tuples > 0) {
 			int blocks = (int) std::min<i64>(div_up<i64>(c.n_tuples, PK_THREADS * PK_ITEMS), (i64) METRO_NUM_SMS_B200 * 8);
-			pack_hist_kernel<<<blocks, PK_THREADS, 0, st>>>(c.d_pid(), c.d_halo(), c.d_type(), (u64) c.n_tuples, (u32) s, L, plan,
+			pack_hist_kernel<<<blocks, PK_THREADS, 0, st>>>(c.d_pid(), c.d_halo(), c.d_type(), (u64) c.n_tuples, (u32) s, ctx->pid_base, L, plan,
 									 keys + off, ctx->sortws.hist);
 			CUDA_TRY(ctx, cudaGetLastError());
 			ctx->launches++;

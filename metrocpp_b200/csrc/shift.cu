@@ -16,13 +16,14 @@
 
 // max pid (for the key width) and range checks of halo index / type, one read of the tuples
 __global__ void tuple_scan_kernel(const u64 *__restrict__ pid, const u32 *__restrict__ halo, const u8 *__restrict__ type,
-				  u64 n, u32 n_halos, u32 nptypes, u64 *out /* [0]=max pid, [1]=#invalid */)
+				  u64 n, u32 n_halos, u32 nptypes, u64 *out /* [0]=max pid, [1]=#invalid, [2]=min pid */)
 {
-	u64 mx = 0;
+	u64 mx = 0, mn = ~0ull;
 	u32 bad = 0;
 	for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
 		const u64 p = pid[i];
 		mx = p > mx ? p : mx;
+		mn = p < mn ? p : mn;
 		if (halo[i] >= n_halos) bad++;
 		if (type && type[i] >= nptypes) bad++;
 	}
@@ -30,10 +31,13 @@ __global__ void tuple_scan_kernel(const u64 *__restrict__ pid, const u32 *__rest
 	for (int off = 16; off > 0; off >>= 1) {
 		const u64 o = __shfl_xor_sync(0xffffffffu, mx, off);
 		mx = o > mx ? o : mx;
+		const u64 o2 = __shfl_xor_sync(0xffffffffu, mn, off);
+		mn = o2 < mn ? o2 : mn;
 		bad += __shfl_xor_sync(0xffffffffu, bad, off);
 	}
 	if ((threadIdx.x & 31) == 0) {
 		atomicMax((unsigned long long *) &out[0], (unsigned long long) mx);
+		atomicMin((unsigned long long *) &out[2], (unsigned long long) mn);
 		if (bad) atomicAdd((unsigned long long *) &out[1], (unsigned long long) bad);
 	}
 }
@@ -41,16 +45,18 @@ __global__ void tuple_scan_kernel(const u64 *__restrict__ pid, const u32 *__rest
 int catalogue_scan_tuples(metro_ctx *ctx, DevCatalogue &c, int nptypes)
 {
 	cudaStream_t st = ctx->stream;
-	u64 *cnt = ctx->counters.as<u64>() + 16;
+	u64 *cnt = ctx->counters.as<u64>() + 16;      // [16],[17],[18]; [18..] is re-used by stage_shift afterwards
 	CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * sizeof(u64), st));
+	CUDA_TRY(ctx, cudaMemsetAsync(cnt + 2, 0xFF, sizeof(u64), st));
 	if (c.n_tuples > 0) {
 		int blocks = (int) std::min<i64>(div_up<i64>(c.n_tuples, TPB), (i64) METRO_NUM_SMS_B200 * 8);
 		tuple_scan_kernel<<<blocks, TPB, 0, st>>>(c.d_pid(), c.d_halo(), c.d_type(), (u64) c.n_tuples, (u32) c.n_halos, (u32) nptypes, cnt);
 		LAUNCHED();
 	}
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 16, cnt, 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 16, cnt, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	c.max_pid = ctx->h_counters[16];
+	c.min_pid = c.n_tuples > 0 ? ctx->h_counters[18] : 0;
 	if (ctx->h_counters[17] != 0) {
 		metro_set_error(ctx, "catalogue has %llu tuples with a halo index >= n_halos or a type >= nptypes",
 				(unsigned long long) ctx->h_counters[17]);
@@ -161,6 +167,7 @@ int stage_shift(metro_ctx *ctx, const metro_params *prm)
 	}
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	n0.max_pid = std::max(c1.max_pid, extra > 0 ? c0.max_pid : (u64) 0);
+	n0.min_pid = c1.n_tuples > 0 ? (extra > 0 ? std::min(c1.min_pid, c0.min_pid) : c1.min_pid) : (extra > 0 ? c0.min_pid : 0);
 	n0.valid = true;
 	// release the old catalogues (owned buffers only)
 	DevBuf *old0[] = {&c0.halo_id, &c0.npart, &c0.npart_tot, &c0.n_orphan_steps, &c0.is_token, &c0.pid, &c0.halo, &c0.type};
