@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmetro_b200.so")
+LIB_PATH = os.environ.get("METRO_B200_LIB") or os.path.join(HERE, "libmetro_b200.so")   # override: tuning variants only
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_COMM = range(6)
 FLAVOUR_GATHER, FLAVOUR_ZOOM_DUP = 0, 1

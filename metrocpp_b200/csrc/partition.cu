@@ -1,0 +1,114 @@
+// partition.cu -- EXPERIMENT (round 1): non-stable 256-way partition pass with fixed-capacity
+// buckets, the building block of an MSD / hash-partition join.  Ranks come from one shared-memory
+// atomic per key (no ballots, no look-back); bucket space is reserved with one global atomic per
+// (tile, bucket).
+#include "context.cuh"
+
+#ifndef PT_THREADS
+#define PT_THREADS 512
+#endif
+#ifndef PT_ITEMS
+#define PT_ITEMS 16
+#endif
+#ifndef PT_MINB
+#define PT_MINB 1
+#endif
+#define PT_TILE (PT_THREADS * PT_ITEMS)
+#define PT_BUCKETS 256
+
+__global__ void __launch_bounds__(PT_THREADS, PT_MINB) partition_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u64 n, int shift, u64 cap,
+							       unsigned long long *gcount /* [256] */, u32 *overflow)
+{
+	extern __shared__ __align__(16) unsigned char psm[];
+	u64 *s_keys = reinterpret_cast<u64 *>(psm);                         // [PT_TILE]
+	i64 *s_dst = reinterpret_cast<i64 *>(s_keys + PT_TILE);             // [256]  global slot of the run minus its tile-local start
+	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + PT_BUCKETS);          // [256]
+	u32 *s_start = s_cnt + PT_BUCKETS;                                  // [256]
+	__shared__ u32 s_warpsum[PT_BUCKETS / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	if (tid < PT_BUCKETS) s_cnt[tid] = 0;
+	__syncthreads();
+	const u64 base = (u64) blockIdx.x * PT_TILE;
+	const u64 wbase = base + (u64) warp * (PT_ITEMS * 32) + lane;
+	u64 key[PT_ITEMS];
+	u32 rk[PT_ITEMS];
+	const bool full = base + PT_TILE <= n;
+#pragma unroll
+	for (int i = 0; i < PT_ITEMS; i++) {
+		const u64 idx = wbase + 32 * i;
+		key[i] = (full || idx < n) ? ld_stream_u64(in + idx) : 0ull;
+	}
+#pragma unroll
+	for (int i = 0; i < PT_ITEMS; i++) {
+		const u32 d = (u32) (key[i] >> shift) & (PT_BUCKETS - 1);
+		rk[i] = (full || wbase + 32 * i < n) ? atomicAdd(&s_cnt[d], 1u) : 0xFFFFFFFFu;
+	}
+	__syncthreads();
+	u32 total = 0, incl = 0;
+	if (tid < PT_BUCKETS) {
+		total = s_cnt[tid];
+		incl = total;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) {
+			u32 v = __shfl_up_sync(0xffffffffu, incl, off);
+			if (lane >= off) incl += v;
+		}
+		if (lane == 31) s_warpsum[warp] = incl;
+	}
+	__syncthreads();
+	if (tid < PT_BUCKETS) {
+		u32 pre = 0;
+#pragma unroll
+		for (int w = 0; w < PT_BUCKETS / 32; w++) pre += (w < warp) ? s_warpsum[w] : 0u;
+		const u32 start = pre + incl - total;
+		s_start[tid] = start;
+		unsigned long long g = total ? atomicAdd(&gcount[tid], (unsigned long long) total) : 0ull;
+		if (g + total > cap) { *overflow = 1; g = 0; }
+		s_dst[tid] = (i64) ((u64) tid * cap + g) - (i64) start;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < PT_ITEMS; i++) {
+		if (rk[i] == 0xFFFFFFFFu) continue;
+		const u32 d = (u32) (key[i] >> shift) & (PT_BUCKETS - 1);
+		s_keys[s_start[d] + rk[i]] = key[i];
+	}
+	__syncthreads();
+	const u32 count = full ? (u32) PT_TILE : (u32) (n - base);
+#pragma unroll 4
+	for (u32 j = tid; j < count; j += PT_THREADS) {
+		const u64 k = s_keys[j];
+		const u32 d = (u32) (k >> shift) & (PT_BUCKETS - 1);
+		st_stream_u64(out + s_dst[d] + (i64) j, k);
+	}
+}
+
+extern "C" int metro_partition_bench(metro_ctx *ctx, const uint64_t *keys_in, uint64_t *keys_out, int64_t n, int shift, int64_t cap, int reps,
+				     float *ms_out, uint64_t *counts_out /* [256] host */)
+{
+	if (!ctx || n <= 0) return METRO_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const size_t smem = (size_t) PT_TILE * 8 + PT_BUCKETS * 8 + PT_BUCKETS * 8;
+	CUDA_TRY(ctx, cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	unsigned long long *g = ctx->counters.as<unsigned long long>();
+	int rc = dev_reserve(ctx, ctx->scratch[0], 257 * 8);
+	if (rc) return rc;
+	g = ctx->scratch[0].as<unsigned long long>();
+	const unsigned tiles = (unsigned) div_up<i64>(n, PT_TILE);
+	float best = 1e30f;
+	for (int r = 0; r < reps; r++) {
+		CUDA_TRY(ctx, cudaMemsetAsync(g, 0, 257 * 8, st));
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
+		partition_kernel<<<tiles, PT_THREADS, smem, st>>>(keys_in, keys_out, (u64) n, shift, (u64) cap, g, reinterpret_cast<u32 *>(g + 256));
+		CUDA_TRY(ctx, cudaGetLastError());
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));
+		CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		float ms;
+		cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
+		if (ms < best) best = ms;
+	}
+	if (ms_out) *ms_out = best;
+	if (counts_out) CUDA_TRY(ctx, cudaMemcpy(counts_out, g, 257 * 8, cudaMemcpyDeviceToHost));
+	return METRO_OK;
+}

@@ -20,8 +20,12 @@
 // ---- tunables (B200: 148 SMs, 227 KB smem/CTA, 64K regs/SM) ----------------------------------
 // 384 threads x 16 keys = 6144-key tile (48 KB of keys in smem) -> 3 CTAs/SM by shared memory,
 // 2-3 by registers; grid = number of tiles, far above 148 x 3, so the tail is < 0.1 %.
+#ifndef OS_THREADS
 #define OS_THREADS 384
+#endif
+#ifndef OS_ITEMS
 #define OS_ITEMS 16
+#endif
 #define OS_TILE (OS_THREADS * OS_ITEMS)
 #define OS_WARPS (OS_THREADS / 32)
 
