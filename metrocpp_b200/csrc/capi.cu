@@ -1,4 +1,6 @@
 // capi.cu -- the extern "C" boundary (include/metro_b200.h) and the per-pair pipeline driver.
+#include <stdlib.h>
+
 #include "context.cuh"
 
 static char g_create_error[512] = "";
@@ -253,22 +255,37 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	res.info.pid_bits = pid_bits; res.info.halo_bits = halo_bits; res.info.type_bits = type_bits; res.info.sort_passes = plan.n_pass;
 	ctx->launches = 0;
 	memset(&ctx->timings, 0, sizeof ctx->timings);
-
-	if ((rc = dev_reserve(ctx, ctx->keys_a, (size_t) N * 8 + 16))) return rc;
-	if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) N * 8 + 16))) return rc;
-	if ((rc = sort_workspace_reserve(ctx, ctx->sortws, N))) return rc;
-
-	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-	if ((rc = stage_pack_hist(ctx, L, plan))) return rc;
-	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
-	u64 *sorted = nullptr;
-	int sort_launches = 0;
-	if ((rc = sort_scatter_passes(ctx, st, ctx->sortws, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), nullptr, nullptr, N, plan, &sorted, nullptr,
-				      ctx->ev_pass, &sort_launches))) return rc;
-	ctx->launches += sort_launches;
-	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+	// Two front ends produce the same pair records:
+	//  * partition join (large pairs): mix(pid) MSD partition x2 + per-bucket shared-memory hash join
+	//  * LSD radix sort by pid + run-length join (any size; also the fallback when a bucket overflows)
 	i64 R = 0, hits = 0;
-	if ((rc = stage_join_count(ctx, L, sorted, N, &R, &hits))) return rc;
+	int sort_launches = 0;
+	PartPlan PP;
+	static const bool force_lsd = getenv("METRO_FORCE_LSD") && atoi(getenv("METRO_FORCE_LSD"));
+	bool part = !force_lsd && partition_join_plan(ctx, L, N, &PP);
+	ctx->timings.path = 0;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+	if (part) {
+		bool fell_back = false;
+		if ((rc = stage_partition_join(ctx, L, PP, &R, &hits, &fell_back))) return rc;
+		if (fell_back) part = false;
+		else { ctx->timings.path = 1; sort_launches = 2; }
+	}
+	if (!part) {
+		if ((rc = dev_reserve(ctx, ctx->keys_a, (size_t) N * 8 + 16))) return rc;
+		if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) N * 8 + 16))) return rc;
+		if ((rc = sort_workspace_reserve(ctx, ctx->sortws, N))) return rc;
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+		if ((rc = stage_pack_hist(ctx, L, plan))) return rc;
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+		u64 *sorted = nullptr;
+		if ((rc = sort_scatter_passes(ctx, st, ctx->sortws, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), nullptr, nullptr, N, plan, &sorted, nullptr,
+					      ctx->ev_pass, &sort_launches))) return rc;
+		ctx->launches += sort_launches;
+		sort_launches = N > 0 ? plan.n_pass : 0;
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+		if ((rc = stage_join_count(ctx, L, sorted, N, &R, &hits))) return rc;
+	}
 	res.info.n_hits = hits;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
 	// multi-GPU: partial pair counts -> owner(haloA) / owner(haloB) (no-op on one GPU)
@@ -301,8 +318,9 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	cudaEventElapsedTime(&tm.join, ctx->ev[2], ctx->ev[3]);
 	cudaEventElapsedTime(&tm.exchange, ctx->ev[3], ctx->ev[7]);
 	cudaEventElapsedTime(&tm.select, ctx->ev[7], ctx->ev[4]);
-	if (N > 0) for (int p = 0; p < plan.n_pass; p++) cudaEventElapsedTime(&tm.sort_pass_ms[p], ctx->ev_pass[p], ctx->ev_pass[p + 1]);
-	tm.sort_launches = N > 0 ? plan.n_pass : 0;
+	if (tm.path == 1) { tm.sort_pass_ms[0] = tm.pack_hist; tm.sort_pass_ms[1] = tm.sort; }
+	else if (N > 0) for (int p = 0; p < plan.n_pass; p++) cudaEventElapsedTime(&tm.sort_pass_ms[p], ctx->ev_pass[p], ctx->ev_pass[p + 1]);
+	tm.sort_launches = sort_launches;
 	tm.total_launches = ctx->launches;
 	res.valid = true;
 	if (info) *info = res.info;

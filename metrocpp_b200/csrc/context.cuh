@@ -61,6 +61,7 @@ struct metro_ctx {
 	DevBuf keys_a, keys_b;          // packed join keys, ping-pong
 	DevBuf table;                   // pair-count hash table (overflow of the per-halo cache)
 	DevBuf pair_cache;              // 4 (tag,count) ways per catalogue-0 halo
+	DevBuf part_counts;             // partition path: bucket fill counters + overflow flag
 	DevBuf scratch[80];             // select pipeline temporaries
 	DevBuf scan_tmp;                // block sums of the scan primitive
 	DevBuf counters;                // small device counters (u64[64])
@@ -86,6 +87,19 @@ int scan_exclusive_u32(metro_ctx *ctx, cudaStream_t st, const u32 *in, u32 *out,
 
 // ---- pipeline stages -----------------------------------------------------------------------------
 int stage_pack_hist(metro_ctx *ctx, const KeyLayout &L, const SortPlan &plan);      // join.cu
+struct PartPlan {
+	int b1, b2;                 // bucket bits of the two levels
+	int r1;                     // level-1 regions are split in r1 replicas (block index mod r1): r1 x fewer atomics per counter
+	int shift1, shift2;         // key >> shift & (2^b - 1)
+	u64 cap1, cap2;             // capacity of a level-1 (bucket, replica) region / a final bucket (keys)
+	u32 tiles1;                 // tiles per level-1 region (= ceil(cap1 / PT_TILE))
+	int pid_bits;
+	u64 mul1, mul2;
+	int xs;
+};
+
+bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out);                       // join.cu
+int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, i64 *n_records, i64 *n_hits, bool *fell_back);
 int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 n,
 		     i64 *n_records, i64 *n_hits);                                     // join.cu
 int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &L, const u64 *recA_key, const u32 *recA_cnt, i64 RA,

@@ -121,3 +121,34 @@ def test_empty_catalogues_and_errors(eng):
         eng.upload(0, prm, bad)
     with pytest.raises(mb.MetroError):
         eng.match_pair(mb.make_params(nptypes=2, fac_orphan_steps=0))
+
+
+def test_partition_join_path_vs_oracle():
+    """The partition-join front end (large pairs) must give the same trees as the oracle; a second
+    engine forced onto the LSD path must agree bit for bit as well."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import os, sys, numpy as np
+sys.path.insert(0, os.getcwd())
+import metrocpp_b200 as mb
+from oracle import binding
+from tests.helpers import compare_result_with_oracle, to_oracle_catalogue
+prm = mb.make_params(nptypes=int(sys.argv[1]), max_orphan_steps=5, flavour=mb.FLAVOUR_GATHER)
+spec = mb.SynthSpec(seed=123, n_halos=6000, n_tuples=3_000_000, pid_bits=24, shard=0, n_shards=1)
+eng = mb.MetroEngine(0)
+eng.synth_pair_device(prm, spec)
+res = eng.find_progenitors_and_clean(prm)
+assert eng.timings()["path"] == int(os.environ.get("EXPECT_PATH", "1")), eng.timings()
+d0, d1 = eng.fetch_catalogue(0), eng.fetch_catalogue(1)
+oprm = binding.Params(prm.nptypes, prm.min_part_cmp, prm.min_part_halo, prm.fac_orphan_steps, prm.max_orphan_steps, 0)
+compare_result_with_oracle(res, binding.match_pair(oprm, to_oracle_catalogue(d0), to_oracle_catalogue(d1)))
+print("PATH_OK", eng.timings()["path"], res.info["n_hits"])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for nptypes in ("2", "6"):
+        for env_extra, expect in (({"METRO_PART_MIN_N": "100000"}, "1"), ({"METRO_FORCE_LSD": "1"}, "0")):
+            env = dict(os.environ, EXPECT_PATH=expect, **env_extra)
+            r = subprocess.run([sys.executable, "-c", code, nptypes], capture_output=True, text=True, cwd=root, env=env, timeout=600)
+            assert r.returncode == 0 and "PATH_OK " + expect in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
