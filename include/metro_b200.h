@@ -105,7 +105,8 @@ typedef struct {
 typedef struct {
 	float total, pack_hist, sort, join, select, exchange;
 	int32_t sort_launches, total_launches;
-	float sort_pass_ms[8];          /* LSD path: per onesweep pass; partition path: [0] = pack+partition A, [1] = partition B */
+	float sort_pass_ms[8];          /* LSD path: per onesweep pass; partition path: [0] = pass A (pack + partition), [1] = pass B (partition),
+	                                 * [2] = pass C (bucket join, hits out), [3] = pass D (hit count) */
 	int32_t path;                   /* 0 = LSD radix sort + run-length join, 1 = partition join */
 } metro_timings;
 

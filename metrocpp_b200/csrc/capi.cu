@@ -269,7 +269,7 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 		bool fell_back = false;
 		if ((rc = stage_partition_join(ctx, L, PP, &R, &hits, &fell_back))) return rc;
 		if (fell_back) part = false;
-		else { ctx->timings.path = 1; sort_launches = 2; }
+		else { ctx->timings.path = 1; sort_launches = 4; }
 	}
 	if (!part) {
 		if ((rc = dev_reserve(ctx, ctx->keys_a, (size_t) N * 8 + 16))) return rc;
@@ -318,7 +318,11 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	cudaEventElapsedTime(&tm.join, ctx->ev[2], ctx->ev[3]);
 	cudaEventElapsedTime(&tm.exchange, ctx->ev[3], ctx->ev[7]);
 	cudaEventElapsedTime(&tm.select, ctx->ev[7], ctx->ev[4]);
-	if (tm.path == 1) { tm.sort_pass_ms[0] = tm.pack_hist; tm.sort_pass_ms[1] = tm.sort; }
+	if (tm.path == 1) {
+		tm.sort_pass_ms[0] = tm.pack_hist; tm.sort_pass_ms[1] = tm.sort;
+		cudaEventElapsedTime(&tm.sort_pass_ms[2], ctx->ev[2], ctx->ev[10]);
+		cudaEventElapsedTime(&tm.sort_pass_ms[3], ctx->ev[10], ctx->ev[3]);
+	}
 	else if (N > 0) for (int p = 0; p < plan.n_pass; p++) cudaEventElapsedTime(&tm.sort_pass_ms[p], ctx->ev_pass[p], ctx->ev_pass[p + 1]);
 	tm.sort_launches = sort_launches;
 	tm.total_launches = ctx->launches;

@@ -1,0 +1,779 @@
+// partjoin.cu -- partition join: the front end for large pairs.
+//
+// Replaces the hot loop of FindProgenitors (reference src/MergerTree.cpp:443-472, run twice per pair
+// from src/main.cpp:199,217).  The join only needs equal particle IDs to MEET, not a total order, and
+// the pair counts only need equal (haloA, haloB) to meet.  So the pipeline is two shuffles, each a
+// streaming partition with shared-memory work in between, and NO global atomics per tuple or per hit:
+//
+//   pass A  pack (12-13 B/tuple in) + 2^b1-way partition on mix(pid)   -> 2^b1 x r1 regions of fixed capacity
+//   pass B  2^b2-way partition of every region                          -> 2^(b1+b2) buckets of 4-8 k keys
+//   pass C  per bucket: shared-memory hash table of the catalogue-1 members, probed by the catalogue-0
+//           members; every match is a hit record (A, B, tA, tB), partitioned in shared memory by halo-A
+//           range and appended to that range's region (8 B/hit out)
+//   pass D  per halo-A range: the hits are counted in shared memory (WAYS (tag,count) slots per halo A,
+//           direct mapped) and leave as (record, count) pairs - what the selection stage consumes
+//
+// mix(pid) is a bijection that spreads any ID distribution uniformly, so the key buckets have FIXED
+// capacity (mean + 9 sigma): no digit histograms, no look-back, no stability requirement.  The hit
+// regions are sized from an exact count of the catalogue-0 tuples per halo range (every hit belongs to
+// one catalogue-0 tuple; 2 hits per tuple + slack are provisioned).  Any overflow (adversarial
+// duplication of one pid, > 2 memberships per particle on average over a whole range) raises a flag and
+// the caller falls back to the LSD sort path of join.cu, which has no such limit.
+#include <stdlib.h>
+
+#include "context.cuh"
+
+#define PT_THREADS 256
+#define PT_ITEMS 16
+#define PT_TILE (PT_THREADS * PT_ITEMS)
+// Fill counters that many blocks bump with global atomics live one per 128-byte line: the L2 atomic
+// unit serialises operations on the same line, not only on the same word.
+#define CSTRIDE 32
+
+// bijection on pid_bits-bit integers (odd multiplies and xor-shifts are invertible mod 2^bits)
+__device__ __forceinline__ u64 mix_pid(u64 x, const PartPlan &P)
+{
+	const u64 mask = P.pid_bits >= 64 ? ~0ull : ((1ull << P.pid_bits) - 1ull);
+	x = (x * P.mul1) & mask;
+	x ^= x >> P.xs;
+	x = (x * P.mul2) & mask;
+	x ^= x >> P.xs;
+	return x;
+}
+
+template <int NB, bool PACK>
+__global__ void __launch_bounds__(PT_THREADS, 3) part_kernel(const u64 *__restrict__ in, const u32 *__restrict__ in_halo, const u8 *__restrict__ in_type,
+							     u64 n, u32 snap, u64 pid_base, KeyLayout L, PartPlan P, u64 *__restrict__ out,
+							     u32 *gcount_in /* level 2: counts of the level-1 regions */,
+							     u32 *gcount_out, u32 *overflow)
+{
+	extern __shared__ __align__(16) unsigned char psm[];
+	u64 *s_keys = reinterpret_cast<u64 *>(psm);                          // [PT_TILE]
+	i64 *s_dst = reinterpret_cast<i64 *>(s_keys + PT_TILE);              // [NB] global slot of a run minus its tile-local start
+	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + NB);                   // [NB]
+	u32 *s_start = s_cnt + NB;                                           // [NB]
+	__shared__ u32 s_warpsum[PT_THREADS / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	constexpr int BPT = NB / PT_THREADS > 0 ? NB / PT_THREADS : 1;       // buckets per thread in the scan
+	for (int i = tid; i < NB; i += PT_THREADS) s_cnt[i] = 0;
+
+	u64 base, count;            // this tile = [base, base + count) of the input stream
+	u64 region = 0;             // level 2: which level-1 region
+	const u64 *src = in;
+	if (PACK) {
+		base = (u64) blockIdx.x * PT_TILE;
+		count = n - base < (u64) PT_TILE ? n - base : (u64) PT_TILE;
+	} else {
+		region = blockIdx.x / P.tiles1;                              // (level-1 bucket, replica)
+		const u64 t = blockIdx.x % P.tiles1;
+		const u64 have = gcount_in[region * CSTRIDE];
+		base = t * PT_TILE;
+		if (base >= have) return;
+		count = have - base < (u64) PT_TILE ? have - base : (u64) PT_TILE;
+		src = in + region * P.cap1;
+	}
+	__syncthreads();
+	const int shift = PACK ? P.shift1 : P.shift2;
+	const u64 wbase = base + (u64) warp * (PT_ITEMS * 32) + lane;
+	u64 key[PT_ITEMS];
+	u32 rk[PT_ITEMS];
+	if (PACK) {
+		// all loads first (plain streaming loads the compiler may hoist), then the arithmetic
+		u32 ht[PT_ITEMS];
+#pragma unroll
+		for (int i = 0; i < PT_ITEMS; i++) {
+			const u64 idx = wbase + 32 * i;
+			const bool ok = idx < base + count;
+			key[i] = ok ? __ldcs(src + idx) : 0ull;
+			ht[i] = ok ? __ldcs(in_halo + idx) : 0u;
+			rk[i] = ok ? (in_type ? (u32) __ldcs(in_type + idx) : 1u) : 0xFFFFFFFFu;     // type for now
+		}
+#pragma unroll
+		for (int i = 0; i < PT_ITEMS; i++) {
+			const bool ok = rk[i] != 0xFFFFFFFFu;
+			key[i] = key_pack(L, mix_pid(key[i] - pid_base, P), snap, ht[i], rk[i] & L.type_mask);
+			rk[i] = ok ? 0u : 0xFFFFFFFFu;
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < PT_ITEMS; i++) {
+			const u64 idx = wbase + 32 * i;
+			const bool ok = idx < base + count;
+			key[i] = ok ? ld_stream_u64(src + idx) : 0ull;
+			rk[i] = ok ? 0u : 0xFFFFFFFFu;
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < PT_ITEMS; i++) {
+		const u32 d = (u32) (key[i] >> shift) & (NB - 1);
+		if (rk[i] == 0u) rk[i] = atomicAdd(&s_cnt[d], 1u);
+	}
+	__syncthreads();
+	// exclusive scan of the NB tile counts (thread t owns buckets [t*BPT, (t+1)*BPT))
+	u32 loc[BPT];
+	u32 sum = 0;
+#pragma unroll
+	for (int k = 0; k < BPT; k++) { loc[k] = (tid * BPT + k) < NB ? s_cnt[tid * BPT + k] : 0u; sum += loc[k]; }
+	u32 incl = sum;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		u32 v = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane >= off) incl += v;
+	}
+	if (lane == 31) s_warpsum[warp] = incl;
+	__syncthreads();
+	u32 pre = 0;
+#pragma unroll
+	for (int w = 0; w < PT_THREADS / 32; w++) pre += (w < warp) ? s_warpsum[w] : 0u;
+	u32 run = pre + incl - sum;
+#pragma unroll
+	for (int k = 0; k < BPT; k++) {
+		const int b = tid * BPT + k;
+		if (b < NB) {
+			// pass A: region (bucket b, replica); pass B: final bucket (level-1 bucket, b) - the replicas merge here
+			const u64 gb = PACK ? (u64) b * P.r1 + (blockIdx.x & (P.r1 - 1)) : (region / P.r1) * NB + (u64) b;
+			const u64 cap = PACK ? P.cap1 : P.cap2;
+			u32 g = loc[k] ? atomicAdd(&gcount_out[PACK ? gb * CSTRIDE : gb], loc[k]) : 0u;
+			if ((u64) g + loc[k] > cap) { *overflow = 1; g = 0; }
+			s_start[b] = run;
+			s_dst[b] = (i64) (gb * cap + g) - (i64) run;
+			run += loc[k];
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int i = 0; i < PT_ITEMS; i++) {
+		if (rk[i] == 0xFFFFFFFFu) continue;
+		const u32 d = (u32) (key[i] >> shift) & (NB - 1);
+		s_keys[s_start[d] + rk[i]] = key[i];
+	}
+	__syncthreads();
+#pragma unroll 4
+	for (u32 j = tid; j < (u32) count; j += PT_THREADS) {
+		const u64 k = s_keys[j];
+		const u32 d = (u32) (k >> shift) & (NB - 1);
+		st_stream_u64(out + s_dst[d] + (i64) j, k);
+	}
+}
+
+// ---- hit regions ------------------------------------------------------------------------------
+// A hit record is the 64-bit pair key the selection stage consumes:
+//   rec = (A << (halo_bits + 2 type_bits)) | tag,   tag = (B << 2 type_bits) | (tA << type_bits) | tB
+// Hit partition d = A >> log_hp (HP = 2^log_hp catalogue-0 halos, the range one pass-D block counts).
+struct HitPlan {
+	int rec_a_shift;            // halo_bits + 2 type_bits
+	int log_hp;                 // halos per hit partition (log2)
+	int ways;                   // (tag,count) slots per halo in pass D
+	u32 nbh;                    // hit partitions
+	u32 slack;                  // fixed part of a region's capacity
+};
+#define HIT_MAX_PARTS 1024
+#define HIT_EMPTY 0xFFFFFFFFu
+
+// exact number of catalogue-0 tuples per hit partition (tuples of a halo are normally contiguous:
+// every thread run-length-compresses its 16 consecutive tuples before touching shared memory)
+#define HC_THREADS 256
+#define HC_ITEMS 16
+__global__ void __launch_bounds__(HC_THREADS) hit_count_kernel(const u32 *__restrict__ halo, u64 n, int log_hp, u32 nbh, int vec, u32 *__restrict__ t0)
+{
+	__shared__ u32 s_bin[HIT_MAX_PARTS];
+	for (u32 i = threadIdx.x; i < nbh; i += HC_THREADS) s_bin[i] = 0;
+	__syncthreads();
+	const u64 base = ((u64) blockIdx.x * HC_THREADS + threadIdx.x) * HC_ITEMS;
+	if (base < n) {
+		u32 h[HC_ITEMS];
+		if (vec && base + HC_ITEMS <= n) {
+			const uint4 *p = reinterpret_cast<const uint4 *>(halo + base);           // base is a multiple of 16 tuples = 64 B
+#pragma unroll
+			for (int q = 0; q < HC_ITEMS / 4; q++) {
+				const uint4 v = __ldg(p + q);
+				h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
+			}
+		} else {
+#pragma unroll
+			for (int q = 0; q < HC_ITEMS; q++) h[q] = base + q < n ? halo[base + q] : 0xFFFFFFFFu;
+		}
+		u32 cur = 0xFFFFFFFFu, c = 0;
+#pragma unroll
+		for (int q = 0; q < HC_ITEMS; q++) {
+			const u32 d = h[q] == 0xFFFFFFFFu ? 0xFFFFFFFFu : h[q] >> log_hp;
+			if (d != cur) {
+				if (c && cur < nbh) atomicAdd(&s_bin[cur], c);
+				cur = d; c = 0;
+			}
+			c++;
+		}
+		if (c && cur < nbh) atomicAdd(&s_bin[cur], c);
+	}
+	__syncthreads();
+	for (u32 i = threadIdx.x; i < nbh; i += HC_THREADS) {
+		const u32 c = s_bin[i];
+		if (c) atomicAdd(&t0[i], c);
+	}
+}
+
+// block-wide exclusive scan of one u64 per thread (1024 threads)
+__device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64 *s_warp /* [32] */, u64 *total)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	u64 incl = v;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		const u64 x = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane >= off) incl += x;
+	}
+	__syncthreads();
+	if (lane == 31) s_warp[warp] = incl;
+	__syncthreads();
+	u64 pre = 0, tot = 0;
+	for (int w = 0; w < (int) (blockDim.x >> 5); w++) { const u64 x = s_warp[w]; if (w < warp) pre += x; tot += x; }
+	if (total) *total = tot;
+	return pre + incl - v;
+}
+
+// region capacity and base per hit partition (1 block of HIT_MAX_PARTS threads)
+__global__ void __launch_bounds__(HIT_MAX_PARTS) hit_plan_kernel(const u32 *__restrict__ t0, u32 nbh, u32 slack, u64 *__restrict__ hit_base,
+								  u32 *__restrict__ hit_cap)
+{
+	__shared__ u64 s_warp[32];
+	const u32 d = threadIdx.x;
+	u64 cap = 0;
+	if (d < nbh) cap = (2ull * t0[d] + slack + 1ull) & ~1ull;
+	if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;                    // 32-bit fill counters; more raises the overflow flag
+	const u64 base = block_excl_scan_u64(cap, s_warp, nullptr);
+	if (d < nbh) { hit_base[d] = base; hit_cap[d] = (u32) cap; }
+}
+
+// ---- pass C: bucket join, hits out --------------------------------------------------------------
+// The catalogue-1 members of a bucket go into a bucketised shared-memory table: BJ_NB1 cells of 4
+// slots, filled through one counter per cell, so a probe is a short scan of one cell (no open-addressing
+// chains).  A full cell (Poisson tail, ~6 % of the members) spills into BJ_NB2 secondary cells, those
+// into a short list.  The catalogue-0 members are compacted into shared memory while the table is
+// built, then probed densely, 512 at a time; the hits are written into the same array behind the read
+// frontier (BJ_SLACK slots of head room for particles with several catalogue-1 memberships).
+// All loops over a bucket are rolled over shared-memory arrays: the kernel stays inside the 32 KB
+// instruction cache (a fully unrolled register version spent most of its time in instruction fetch).
+#define BJ_THREADS 512
+#define BJ_NB1 1536             // primary cells x 4 slots
+#define BJ_NB2 256              // secondary cells x 4 slots
+#define BJ_N3 32                // last-resort list
+#define BJ_SH 6144              // staging array: [BJ_SLACK][catalogue-0 members]; == 4 * BJ_NB1: the dead table is the sorted buffer
+#define BJ_SLACK 1536
+#define BJ_KPT 18               // keys per thread: cap2 <= BJ_THREADS * BJ_KPT
+#define BJ_BK 6                 // keys per thread and load batch
+#define BJ_SMEM ((size_t) BJ_NB1 * 32 + (size_t) BJ_SH * 8 + (size_t) HIT_MAX_PARTS * 16)
+
+__global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ gcount, u64 cap2, KeyLayout L,
+								    u64 rmask, HitPlan hp, const u64 *__restrict__ hit_base,
+								    const u32 *__restrict__ hit_cap, u32 *hit_cnt, u64 *__restrict__ hits_out,
+								    u64 *counters, u32 *overflow)
+{
+	extern __shared__ __align__(16) unsigned char bsm[];
+	u64 *t1 = reinterpret_cast<u64 *>(bsm);                              // [BJ_NB1 * 4] primary cells; later the hits sorted by partition
+	u64 *stage = t1 + BJ_NB1 * 4;                                        // [BJ_SH] catalogue-0 members, overwritten by the hits
+	unsigned char *un = reinterpret_cast<unsigned char *>(stage + BJ_SH); // 16 KB used twice:
+	u64 *t2 = reinterpret_cast<u64 *>(un);                               //   build/probe: [BJ_NB2 * 4] secondary cells
+	u64 *t3 = t2 + BJ_NB2 * 4;                                           //                [BJ_N3]
+	u32 *cnt1 = reinterpret_cast<u32 *>(t3 + BJ_N3);                     //                [BJ_NB1]
+	u32 *cnt2 = cnt1 + BJ_NB1;                                           //                [BJ_NB2]
+	i64 *s_dst = reinterpret_cast<i64 *>(un);                            //   hit partition: [HIT_MAX_PARTS] global slot of a run minus its local start
+	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + HIT_MAX_PARTS);        //                  [HIT_MAX_PARTS] counts, then write cursors
+	static_assert((size_t) BJ_NB2 * 32 + BJ_N3 * 8 + (BJ_NB1 + BJ_NB2) * 4 <= (size_t) HIT_MAX_PARTS * 16, "union overflow");
+	static_assert(BJ_SH == BJ_NB1 * 4 && BJ_KPT % BJ_BK == 0, "layout");
+	__shared__ u32 s_n0, s_n3, s_nhits, s_warpsum[BJ_THREADS / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const u64 g = blockIdx.x;
+	const u32 n = gcount[g];
+	if (n == 0 || (u64) n > cap2) return;                                // overflow was flagged by the partition pass already
+	const u64 *src = keys + g * cap2;
+	for (int i = tid; i < BJ_NB1 + BJ_NB2; i += BJ_THREADS) cnt1[i] = 0; // cnt2 follows cnt1
+	if (tid == 0) { s_n0 = 0; s_n3 = 0; s_nhits = 0; }
+	u32 ovf = 0;                // overflow causes: 2 table full, 4 staging full, 8 hit region full
+	u64 *keys0 = stage + BJ_SLACK;
+	// build: the first loads fly while the counters are being cleared
+#pragma unroll 1
+	for (int bt = 0; bt < BJ_KPT / BJ_BK; bt++) {
+		u64 key[BJ_BK];
+#pragma unroll
+		for (int i = 0; i < BJ_BK; i++) {
+			const u32 j = tid + (bt * BJ_BK + i) * BJ_THREADS;
+			key[i] = j < n ? ld_stream_u64(src + j) : 0ull;
+		}
+		if (bt == 0) __syncthreads();
+#pragma unroll
+		for (int i = 0; i < BJ_BK; i++) {
+			const bool valid = (tid + (bt * BJ_BK + i) * BJ_THREADS) < n;
+			const bool is1 = valid && key_snap(L, key[i]) != 0;
+			const u32 b0 = __ballot_sync(0xffffffffu, valid && !is1);
+			if (b0) {
+				u32 base = 0;
+				if (lane == 0) base = atomicAdd(&s_n0, (u32) __popc(b0));
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (valid && !is1) {
+					const u32 pos = base + __popc(b0 & lanemask_lt());
+					if (pos < BJ_SH - BJ_SLACK) keys0[pos] = key[i];
+				}
+			}
+			if (is1) {
+				const u64 hh = (key_pid(L, key[i]) & rmask) * 0x9E3779B97F4A7C15ull;
+				const u32 c1 = (u32) (((hh >> 32) * BJ_NB1) >> 32);
+				const u32 p1 = atomicAdd(&cnt1[c1], 1u);
+				if (p1 < 4) t1[c1 * 4 + p1] = key[i];
+				else {
+					const u32 c2 = (u32) (hh >> 20) & (BJ_NB2 - 1);
+					const u32 p2 = atomicAdd(&cnt2[c2], 1u);
+					if (p2 < 4) t2[c2 * 4 + p2] = key[i];
+					else {
+						const u32 p3 = atomicAdd(&s_n3, 1u);
+						if (p3 < BJ_N3) t3[p3] = key[i];
+						else ovf |= 2u;
+					}
+				}
+			}
+		}
+	}
+	__syncthreads();
+	u32 n0 = s_n0;
+	if (n0 > BJ_SH - BJ_SLACK) { ovf |= 4u; n0 = BJ_SH - BJ_SLACK; }
+	const u32 n3 = s_n3 < BJ_N3 ? s_n3 : BJ_N3;
+	// probe: every match of a catalogue-0 member is one hit
+	const int tb = L.type_bits;
+	const u32 a_max = (hp.nbh << hp.log_hp) - 1u;                        // keeps the partition of a clobbered key in range after an overflow
+#pragma unroll 1
+	for (u32 r0 = 0; r0 < n0; r0 += BJ_THREADS) {
+		const bool valid = r0 + tid < n0;
+		u64 recA = 0, pid = 0, hh = 0, first = 0, second = 0;
+		u32 m = 0;
+		// scans the cells of `pid`: the primary one, then (only if it was full) the secondary one, then the list;
+		// matches number `skip` and later are passed to f
+		auto scan = [&](u32 skip, auto f) {
+			const u64 *cell = t1 + (u32) (((hh >> 32) * BJ_NB1) >> 32) * 4;
+			u32 kc = cnt1[(u32) (((hh >> 32) * BJ_NB1) >> 32)], seen = 0;
+			int lvl = 0;
+			for (;;) {
+				const u32 kn = lvl < 2 ? (kc < 4 ? kc : 4) : kc;
+				for (u32 k = 0; k < kn; k++) {
+					const u64 e = cell[k];
+					if (key_pid(L, e) == pid) {
+						if (seen >= skip) f(recA | ((u64) key_halo(L, e) << (2 * tb)) | (u64) key_type(L, e));
+						seen++;
+					}
+				}
+				if (lvl == 2 || kc <= 4) break;
+				if (lvl == 0) {
+					const u32 c2 = (u32) (hh >> 20) & (BJ_NB2 - 1);
+					cell = t2 + c2 * 4; kc = cnt2[c2]; lvl = 1;
+				} else { cell = t3; kc = n3; lvl = 2; }
+			}
+		};
+		if (valid) {
+			const u64 k0 = keys0[r0 + tid];
+			pid = key_pid(L, k0);
+			u32 A = key_halo(L, k0);
+			A = A < a_max ? A : a_max;
+			recA = ((u64) A << hp.rec_a_shift) | ((u64) key_type(L, k0) << tb);
+			hh = (pid & rmask) * 0x9E3779B97F4A7C15ull;
+			scan(0, [&](u64 rec) { if (m == 0) first = rec; else if (m == 1) second = rec; m++; });
+		}
+		__syncthreads();                                             // every member of this round is in registers: its slots may take hits
+		const u32 ballot = __ballot_sync(0xffffffffu, m > 0);
+		if (ballot) {
+			u32 b = 0;
+			if (lane == 0) b = atomicAdd(&s_nhits, (u32) __popc(ballot));
+			b = __shfl_sync(0xffffffffu, b, 0);
+			if (m > 0) {
+				const u32 pos = b + __popc(ballot & lanemask_lt());
+				if (pos < BJ_SH) stage[pos] = first;
+			}
+		}
+		if (m > 1) {
+			const u32 pos = atomicAdd(&s_nhits, m - 1);
+			if (pos < BJ_SH) stage[pos] = second;
+			if (m > 2) {                                                 // three or more memberships: rescan for the rest
+				u32 q = pos + 1;
+				scan(2, [&](u64 rec) { if (q < BJ_SH) stage[q] = rec; q++; });
+			}
+		}
+		// hits so far must stay behind the read frontier of the next round
+		__syncwarp();
+		if (*reinterpret_cast<volatile u32 *>(&s_nhits) > BJ_SLACK + r0 + BJ_THREADS && r0 + BJ_THREADS < n0) ovf |= 4u;
+	}
+	__syncthreads();                                                     // table and counters are dead from here on
+	u32 nh = s_nhits;
+	if (nh > BJ_SH) { ovf |= 4u; nh = BJ_SH; }
+	if (tid == 0 && nh) atomicAdd((unsigned long long *) &counters[0], (unsigned long long) nh);
+	for (u32 i = tid; i < hp.nbh; i += BJ_THREADS) s_cnt[i] = 0;
+	__syncthreads();
+	// hits per partition
+	const int psh = hp.rec_a_shift + hp.log_hp;
+	for (u32 j = tid; j < nh; j += BJ_THREADS) atomicAdd(&s_cnt[(u32) (stage[j] >> psh)], 1u);
+	__syncthreads();
+	// exclusive scan of the partition counts (2 per thread), region space reserved with one global atomic each
+	constexpr int BPT = HIT_MAX_PARTS / BJ_THREADS;
+	u32 loc[BPT], sum = 0;
+#pragma unroll
+	for (int k = 0; k < BPT; k++) { const u32 b = tid * BPT + k; loc[k] = b < hp.nbh ? s_cnt[b] : 0u; sum += loc[k]; }
+	u32 incl = sum;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		const u32 v = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane >= off) incl += v;
+	}
+	if (lane == 31) s_warpsum[warp] = incl;
+	__syncthreads();
+	u32 pre = 0;
+#pragma unroll
+	for (int w = 0; w < BJ_THREADS / 32; w++) pre += (w < warp) ? s_warpsum[w] : 0u;
+	u32 run = pre + incl - sum;
+#pragma unroll
+	for (int k = 0; k < BPT; k++) {
+		const u32 b = tid * BPT + k;
+		if (b < hp.nbh) {
+			i64 dst = INT64_MIN;
+			if (loc[k]) {
+				const u32 g0 = atomicAdd(&hit_cnt[b * CSTRIDE], loc[k]);
+				if ((u64) g0 + loc[k] <= (u64) hit_cap[b]) dst = (i64) (hit_base[b] + g0) - (i64) run;
+				else ovf |= 8u;
+			}
+			s_dst[b] = dst;
+			s_cnt[b] = run;                                              // write cursor of the partition inside the sorted buffer
+			run += loc[k];
+		}
+	}
+	__syncthreads();
+	for (u32 j = tid; j < nh; j += BJ_THREADS) {
+		const u64 r = stage[j];
+		t1[atomicAdd(&s_cnt[(u32) (r >> psh)], 1u)] = r;
+	}
+	__syncthreads();
+	for (u32 j = tid; j < nh; j += BJ_THREADS) {
+		const u64 r = t1[j];
+		const i64 dst = s_dst[(u32) (r >> psh)];
+		if (dst != INT64_MIN) st_stream_u64(hits_out + dst + (i64) j, r);
+	}
+	if (ovf) atomicOr(overflow, ovf);
+}
+
+// ---- pass D: count the hits of one halo-A range in shared memory -------------------------------
+// Work units: a partition, or a slice of a heavy one (a catalogue dominated by one halo); slices of
+// the same partition emit separate records for the same pair, which the selection stage sums.
+#define HR_THREADS 512
+#define HR_OVF 4096             // entries of the per-block hash table for pairs beyond a halo's WAYS slots
+#define HR_OVF_PROBES 32
+#define HR_MAX_UNITS (2 * HIT_MAX_PARTS)   // sum of ceil(c_d / (3 mean)) <= nbh + nbh / 3
+
+__global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__restrict__ hit_cnt, u32 nbh, uint4 *__restrict__ units, u32 *n_units)
+{
+	__shared__ u64 s_warp[32];
+	const u32 d = threadIdx.x;
+	const u64 c = d < nbh ? hit_cnt[d * CSTRIDE] : 0;
+	u64 total;
+	block_excl_scan_u64(c, s_warp, &total);
+	u64 slice_max = 3 * (total / nbh) + 1;                          // only partitions well above the mean are split
+	if (slice_max < 65536) slice_max = 65536;
+	const u64 nsl = c ? (c + slice_max - 1) / slice_max : 0;
+	u64 tot_units;
+	const u64 off = block_excl_scan_u64(nsl, s_warp, &tot_units);
+	for (u64 s = 0; s < nsl; s++) units[off + s] = make_uint4(d, (u32) s, (u32) nsl, 0u);
+	if (d == 0) *n_units = (u32) tot_units;
+}
+
+template <int WAYS>
+__global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__restrict__ hits, const u64 *__restrict__ hit_base,
+								 const u32 *__restrict__ hit_cnt, const uint4 *__restrict__ units,
+								 const u32 *__restrict__ n_units, HitPlan hp, u64 *__restrict__ rec_key,
+								 u32 *__restrict__ rec_cnt, u64 rec_cap, u64 *counters, u32 *overflow)
+{
+	if (blockIdx.x >= *n_units) return;
+	extern __shared__ __align__(16) unsigned char hsm[];
+	const u32 HP = 1u << hp.log_hp;
+	u32 *s_tag = reinterpret_cast<u32 *>(hsm);                           // [HP * WAYS]
+	u32 *s_count = s_tag + (size_t) HP * WAYS;                           // [HP * WAYS]
+	u64 *s_okey = reinterpret_cast<u64 *>(s_count + (size_t) HP * WAYS); // [HR_OVF] pairs whose halo ran out of ways: open addressing on the record
+	u32 *s_ocnt = reinterpret_cast<u32 *>(s_okey + HR_OVF);              // [HR_OVF]
+	__shared__ u32 s_warpsum[HR_THREADS / 32];
+	__shared__ u64 s_base;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint4 u = units[blockIdx.x];
+	const u32 d = u.x;
+	const u64 cnt = hit_cnt[d * CSTRIDE];
+	u64 per = (cnt + u.z - 1) / u.z;
+	per = (per + 1) & ~1ull;
+	const u64 lo = (u64) u.y * per, hi = lo + per < cnt ? lo + per : cnt;
+	for (u32 i = tid; i < HP * WAYS; i += HR_THREADS) { s_tag[i] = HIT_EMPTY; s_count[i] = 0; }
+	for (u32 i = tid; i < HR_OVF; i += HR_THREADS) { s_okey[i] = ~0ull; s_ocnt[i] = 0; }
+	__syncthreads();
+	const u64 *src = hits + hit_base[d];
+	const u32 tag_mask = (u32) ((1ull << hp.rec_a_shift) - 1ull);
+	u32 spilled = 0;
+	bool ovf = false;           // record buffer full (cause 16)
+	constexpr int UNR = 4;
+	for (u64 j0 = lo + tid; j0 < hi; j0 += (u64) HR_THREADS * UNR) {
+		u64 r[UNR];
+#pragma unroll
+		for (int q = 0; q < UNR; q++) {
+			const u64 j = j0 + (u64) q * HR_THREADS;
+			r[q] = j < hi ? ld_stream_u64(src + j) : ~0ull;
+		}
+#pragma unroll
+		for (int q = 0; q < UNR; q++) {
+			if (r[q] == ~0ull) continue;
+			const u32 a = (u32) (r[q] >> hp.rec_a_shift) & (HP - 1u);
+			const u32 tag = (u32) r[q] & tag_mask;
+			u32 *tg = s_tag + (size_t) a * WAYS;
+			int w = -1;
+			if (WAYS == 4) {
+				const uint4 t4 = *reinterpret_cast<const uint4 *>(tg);
+				w = t4.x == tag ? 0 : t4.y == tag ? 1 : t4.z == tag ? 2 : t4.w == tag ? 3 : -1;
+			} else if (WAYS == 2) {
+				const uint2 t2 = *reinterpret_cast<const uint2 *>(tg);
+				w = t2.x == tag ? 0 : t2.y == tag ? 1 : -1;
+			}
+			if (w < 0) {
+				// first sight of this partner (or a race with its first sight): claim an empty way
+#pragma unroll
+				for (int x = 0; x < WAYS; x++) {
+					u32 cur = *reinterpret_cast<volatile u32 *>(tg + x);
+					if (cur == HIT_EMPTY) {
+						cur = atomicCAS(tg + x, HIT_EMPTY, tag);
+						if (cur == HIT_EMPTY) cur = tag;
+					}
+					if (cur == tag) { w = x; break; }
+				}
+			}
+			if (w >= 0) atomicAdd(s_count + (size_t) a * WAYS + w, 1u);
+			else {
+				u32 h = (u32) ((r[q] * 0x9E3779B97F4A7C15ull) >> 52) & (HR_OVF - 1);
+				int probe = 0;
+				for (; probe < HR_OVF_PROBES; probe++) {
+					u64 cur = *reinterpret_cast<volatile u64 *>(s_okey + h);
+					if (cur == ~0ull) {
+						cur = atomicCAS((unsigned long long *) (s_okey + h), ~0ull, (unsigned long long) r[q]);
+						if (cur == ~0ull) cur = r[q];
+					}
+					if (cur == r[q]) { atomicAdd(s_ocnt + h, 1u); break; }
+					h = (h + 1) & (HR_OVF - 1);
+				}
+				if (probe == HR_OVF_PROBES) {
+					// last resort: a (record, 1) pair straight to the output
+					const u64 o = atomicAdd((unsigned long long *) &counters[2], 1ull);
+					if (o < rec_cap) { rec_key[o] = r[q]; rec_cnt[o] = 1u; }
+					else ovf = true;
+				}
+				spilled++;
+			}
+		}
+	}
+	__syncthreads();
+	// emit the live ways + the overflow list
+	u32 live = 0;
+	for (u32 i = tid; i < HP * WAYS; i += HR_THREADS) live += s_tag[i] != HIT_EMPTY;
+	for (u32 i = tid; i < HR_OVF; i += HR_THREADS) live += s_okey[i] != ~0ull;
+	u32 incl = live;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		const u32 v = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane >= off) incl += v;
+	}
+	if (lane == 31) s_warpsum[warp] = incl;
+	__syncthreads();
+	u32 pre = 0, tot = 0;
+#pragma unroll
+	for (int x = 0; x < HR_THREADS / 32; x++) { const u32 v = s_warpsum[x]; pre += x < warp ? v : 0u; tot += v; }
+	if (tid == 0) s_base = tot ? atomicAdd((unsigned long long *) &counters[2], (unsigned long long) tot) : 0ull;
+	__syncthreads();
+	u64 o = s_base + pre + incl - live;
+	if (s_base + tot > rec_cap) ovf = true;
+	else {
+		for (u32 i = tid; i < HP * WAYS; i += HR_THREADS) {
+			const u32 t = s_tag[i];
+			if (t != HIT_EMPTY) {
+				rec_key[o] = ((u64) (d * HP + i / WAYS) << hp.rec_a_shift) | (u64) t;
+				rec_cnt[o] = s_count[i];
+				o++;
+			}
+		}
+		for (u32 i = tid; i < HR_OVF; i += HR_THREADS) {
+			const u64 k = s_okey[i];
+			if (k != ~0ull) { rec_key[o] = k; rec_cnt[o] = s_ocnt[i]; o++; }
+		}
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) spilled += __shfl_xor_sync(0xffffffffu, spilled, off);
+	if (lane == 0 && spilled) atomicAdd((unsigned long long *) &counters[5], (unsigned long long) spilled);
+	if (ovf) atomicOr(overflow, 16u);
+}
+
+static size_t part_smem(int nb) { return (size_t) PT_TILE * 8 + (size_t) nb * 16; }
+
+// Is the partition path applicable, and with which bucket bits?
+bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out)
+{
+	static const i64 min_n = getenv("METRO_PART_MIN_N") ? atoll(getenv("METRO_PART_MIN_N")) : (1ll << 23);
+	if (N < min_n || L.pid_bits < 16) return false;                 // small pairs: the LSD path is fine
+	if (L.halo_bits + 2 * L.type_bits > 31) return false;           // the pass-D way tag (B, tA, tB) is 31 bits
+	if (ctx->cat[0].n_halos > (i64) HIT_MAX_PARTS * 8192) return false;
+	int tb = 0;
+	const i64 nmax = std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
+	while (((N >> tb) > 8000 || (nmax >> tb) > 4000) && tb < 20) tb++;   // final buckets of ~4-8 k keys, <= 4 k of either catalogue
+	PartPlan P;
+	P.b1 = tb > 18 ? tb - 9 : (tb + 1) / 2;
+	P.b2 = tb - P.b1;
+	if (P.b1 < 8) P.b1 = 8;
+	if (P.b2 < 8) P.b2 = 8;
+	if (P.b1 > 10 || P.b2 > 10 || P.b1 + P.b2 > L.pid_bits) return false;
+	P.pid_bits = L.pid_bits;
+	P.shift1 = L.pid_shift + L.pid_bits - P.b1;
+	P.shift2 = P.shift1 - P.b2;
+	P.r1 = 8;
+	const double m1 = (double) N / (double) ((1ll << P.b1) * P.r1), m2 = (double) N / (double) (1ll << (P.b1 + P.b2));
+	P.cap1 = (u64) (m1 + 8.0 * sqrt(m1) + 4096.0);
+	P.cap1 = (P.cap1 + 1) & ~1ull;                                  // keep regions 16-byte aligned
+	P.cap2 = (u64) (m2 + 9.0 * sqrt(m2) + 64.0);
+	P.cap2 = (P.cap2 + 1) & ~1ull;
+	if (P.cap2 > (u64) BJ_THREADS * BJ_KPT) return false;
+	P.tiles1 = (u32) div_up<u64>(P.cap1, PT_TILE);
+	P.mul1 = 0x9E3779B97F4A7C15ull; P.mul2 = 0xD6E8FEB86659FD93ull;
+	P.xs = (L.pid_bits + 1) / 2;
+	*out = P;
+	return true;
+}
+
+static HitPlan make_hit_plan(const KeyLayout &L, i64 H0)
+{
+	HitPlan hp;
+	hp.rec_a_shift = L.halo_bits + 2 * L.type_bits;
+	hp.ways = 4; hp.log_hp = 11;                                    // 2048 halos x 4 ways x 8 B = 64 KB: two pass-D blocks per SM
+	auto parts = [&](int lg) { return (u64) div_up<i64>(std::max<i64>(H0, 1), 1ll << lg); };
+	if (parts(hp.log_hp) > HIT_MAX_PARTS) { hp.ways = 2; hp.log_hp = 12; }
+	while (parts(hp.log_hp) > HIT_MAX_PARTS && hp.log_hp < 13) hp.log_hp++;
+	hp.nbh = (u32) parts(hp.log_hp);
+	hp.slack = 2048;
+	return hp;
+}
+
+template <bool PACK>
+static int launch_part(metro_ctx *ctx, int bits, unsigned grid, const u64 *in, const u32 *ih, const u8 *it, u64 n, u32 snap, const KeyLayout &L,
+		       const PartPlan &P, u64 *out, u32 *gin, u32 *gout, u32 *ovf)
+{
+	cudaStream_t st = ctx->stream;
+	const size_t smem = part_smem(1 << bits);
+#define PART_CASE(NB)                                                                                                               \
+	case NB: {                                                                                                                  \
+		static bool attr = false;                                                                                           \
+		if (!attr) { CUDA_TRY(ctx, cudaFuncSetAttribute(part_kernel<NB, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr = true; } \
+		part_kernel<NB, PACK><<<grid, PT_THREADS, smem, st>>>(in, ih, it, n, snap, ctx->pid_base, L, P, out, gin, gout, ovf);   \
+		break;                                                                                                              \
+	}
+	switch (1 << bits) {
+		PART_CASE(256) PART_CASE(512) PART_CASE(1024)
+	default: metro_set_error(ctx, "unsupported partition width 2^%d", bits); return METRO_ERR_UNSUPPORTED;
+	}
+#undef PART_CASE
+	CUDA_TRY(ctx, cudaGetLastError());
+	ctx->launches++;
+	return METRO_OK;
+}
+
+template <int WAYS>
+static int launch_reduce(metro_ctx *ctx, const HitPlan &hp, const u64 *hits, const u64 *hit_base, const u32 *hit_cnt, const uint4 *units, const u32 *n_units,
+			 u64 *rec_key, u32 *rec_cnt, u64 rec_cap, u32 *ovf)
+{
+	const size_t smem = ((size_t) WAYS << hp.log_hp) * 8 + (size_t) HR_OVF * 12;
+	static size_t attr = 0;
+	if (attr < smem) { CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<WAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr = smem; }
+	hit_reduce_kernel<WAYS><<<HR_MAX_UNITS, HR_THREADS, smem, ctx->stream>>>(hits, hit_base, hit_cnt, units, n_units, hp, rec_key, rec_cnt, rec_cap,
+										   ctx->counters.as<u64>(), ovf);
+	CUDA_TRY(ctx, cudaGetLastError());
+	ctx->launches++;
+	return METRO_OK;
+}
+
+// Whole front end of a pair on the partition path: records (scratch[0] = key u64[R], scratch[1] =
+// count u32[R]; the same pair may appear more than once).  *fell_back = true: an overflow flag was
+// raised (nothing usable was produced; the caller runs the LSD path).  Timing events: ev[1] after
+// pass A, ev[2] after pass B, ev[10] after pass C (pass D ends at the caller's ev[3]).
+int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, i64 *n_records, i64 *n_hits, bool *fell_back)
+{
+	cudaStream_t st = ctx->stream;
+	*fell_back = false;
+	const DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
+	const u64 nb1 = (1ull << P.b1) * P.r1, nb = 1ull << (P.b1 + P.b2);     // level-1 regions, final buckets
+	const HitPlan hp = make_hit_plan(L, c0.n_halos);
+	const u64 hits_cap = 2ull * (u64) c0.n_tuples + (u64) (hp.slack + 2) * hp.nbh;
+	const u64 rec_cap = 16ull * (u64) (c0.n_halos + c1.n_halos) + (1ull << 20);
+	int rc;
+	// keys_a: level-1 regions, dead after pass B and reused for the hit regions
+	if ((rc = dev_reserve(ctx, ctx->keys_a, std::max((size_t) nb1 * P.cap1, (size_t) hits_cap) * 8 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) nb * P.cap2 * 8 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->scratch[0], (size_t) rec_cap * sizeof(u64)))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->scratch[1], (size_t) rec_cap * sizeof(u32)))) return rc;
+	// small state: [g1 nb1*CSTRIDE][hit_cnt 1024*CSTRIDE][g2 nb][t0 1024][hit_cap 1024][ovf, n_units, pad..16] u32, then hit_base u64[1024],
+	// units uint4[HR_MAX_UNITS]
+	const size_t n32 = (size_t) nb1 * CSTRIDE + (size_t) HIT_MAX_PARTS * CSTRIDE + nb + 2 * HIT_MAX_PARTS + 16;
+	const size_t off_base = (n32 * 4 + 15) & ~(size_t) 15;
+	const size_t off_units = off_base + (size_t) HIT_MAX_PARTS * 8;
+	if ((rc = dev_reserve(ctx, ctx->part_counts, off_units + (size_t) HR_MAX_UNITS * 16))) return rc;
+	u32 *g1 = ctx->part_counts.as<u32>(), *hit_cnt = g1 + nb1 * CSTRIDE, *g2 = hit_cnt + (size_t) HIT_MAX_PARTS * CSTRIDE, *t0 = g2 + nb, *hit_cap = t0 + HIT_MAX_PARTS;
+	u32 *ovf = hit_cap + HIT_MAX_PARTS, *n_units = ovf + 1;
+	u64 *hit_base = reinterpret_cast<u64 *>(ctx->part_counts.as<unsigned char>() + off_base);
+	uint4 *units = reinterpret_cast<uint4 *>(ctx->part_counts.as<unsigned char>() + off_units);
+	u64 *counters = ctx->counters.as<u64>();
+	CUDA_TRY(ctx, cudaMemsetAsync(g1, 0, n32 * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 8 * sizeof(u64), st));
+	// hit regions: exact catalogue-0 tuple count per halo range -> capacity and base
+	if (c0.n_tuples > 0) {
+		hit_count_kernel<<<(unsigned) div_up<i64>(c0.n_tuples, HC_THREADS * HC_ITEMS), HC_THREADS, 0, st>>>(c0.d_halo(), (u64) c0.n_tuples, hp.log_hp, hp.nbh,
+												    ((uintptr_t) c0.d_halo() & 15) == 0, t0);
+		CUDA_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
+	}
+	hit_plan_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(t0, hp.nbh, hp.slack, hit_base, hit_cap);
+	CUDA_TRY(ctx, cudaGetLastError());
+	ctx->launches++;
+	// pass A: both catalogues (catalogue 0 first; the order inside a bucket is irrelevant)
+	for (int s = 0; s < 2; s++) {
+		const DevCatalogue &c = ctx->cat[s];
+		if (c.n_tuples == 0) continue;
+		if ((rc = launch_part<true>(ctx, P.b1, (unsigned) div_up<i64>(c.n_tuples, PT_TILE), c.d_pid(), c.d_halo(), c.d_type(), (u64) c.n_tuples, (u32) s, L, P,
+					    ctx->keys_a.as<u64>(), nullptr, g1, ovf))) return rc;
+	}
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+	// pass B
+	if ((rc = launch_part<false>(ctx, P.b2, (unsigned) (nb1 * P.tiles1), ctx->keys_a.as<u64>(), nullptr, nullptr, 0, 0, L, P, ctx->keys_b.as<u64>(), g1, g2,
+				     ovf))) return rc;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+	// pass C
+	{
+		static bool attr = false;
+		if (!attr) { CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BJ_SMEM)); attr = true; }
+		const int rb = L.pid_bits - P.b1 - P.b2;
+		const u64 rmask = rb >= 64 ? ~0ull : ((1ull << rb) - 1ull);
+		bucket_join_kernel<<<(unsigned) nb, BJ_THREADS, BJ_SMEM, st>>>(ctx->keys_b.as<u64>(), g2, P.cap2, L, rmask, hp, hit_base, hit_cap, hit_cnt,
+										ctx->keys_a.as<u64>(), counters, ovf);
+		CUDA_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
+	}
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[10], st));
+	// pass D
+	hit_units_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(hit_cnt, hp.nbh, units, n_units);
+	CUDA_TRY(ctx, cudaGetLastError());
+	ctx->launches++;
+	if (hp.ways == 4) rc = launch_reduce<4>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
+	else rc = launch_reduce<2>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
+	if (rc) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 60, ovf, 4, cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	if (*reinterpret_cast<u32 *>(ctx->h_counters + 60) != 0) {
+		static const bool dbg = getenv("METRO_DEBUG") != nullptr;
+		if (dbg) fprintf(stderr, "[metro] partition join fell back to the LSD path: overflow mask 0x%x (1 key region, 2 bucket table, 4 hit staging, "
+				 "8 hit region, 16 record buffer)\n", *reinterpret_cast<u32 *>(ctx->h_counters + 60));
+		*fell_back = true;
+		return METRO_OK;
+	}
+	*n_hits = (i64) ctx->h_counters[0];
+	*n_records = (i64) ctx->h_counters[2];
+	ctx->res.info.n_table_hits = (i64) ctx->h_counters[5];
+	return METRO_OK;
+}
