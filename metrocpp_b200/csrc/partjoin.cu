@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(PT_THREADS, 3) part_kernel(const u64 *__restri
 	for (int k = 0; k < BPT; k++) {
 		const int b = tid * BPT + k;
 		if (b < NB) {
-			// pass A: region (bucket b, replica); pass B: final bucket (level-1 bucket, b) - the replicas merge here
-			const u64 gb = PACK ? (u64) b * P.r1 + (blockIdx.x & (P.r1 - 1)) : (region / P.r1) * NB + (u64) b;
+			// pass A: region (catalogue, bucket b, replica); pass B: final bucket (catalogue, level-1 bucket, b) - the replicas merge here
+			const u64 gb = PACK ? (((u64) snap << P.b1) + (u64) b) * P.r1 + (blockIdx.x & (P.r1 - 1)) : (region / P.r1) * NB + (u64) b;
 			const u64 cap = PACK ? P.cap1 : P.cap2;
 			u32 g = loc[k] ? atomicAdd(&gcount_out[PACK ? gb * CSTRIDE : gb], loc[k]) : 0u;
 			if ((u64) g + loc[k] > cap) { *overflow = 1; g = 0; }
@@ -245,32 +245,34 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_plan_kernel(const u32 *__re
 }
 
 // ---- pass C: bucket join, hits out --------------------------------------------------------------
-// The catalogue-1 members of a bucket go into a bucketised shared-memory table: BJ_NB1 cells of 4
-// slots, filled through one counter per cell, so a probe is a short scan of one cell (no open-addressing
-// chains).  A full cell (Poisson tail, ~6 % of the members) spills into BJ_NB2 secondary cells, those
-// into a short list.  The catalogue-0 members are compacted into shared memory while the table is
-// built, then probed densely, 512 at a time; the hits are written into the same array behind the read
-// frontier (BJ_SLACK slots of head room for particles with several catalogue-1 memberships).
-// All loops over a bucket are rolled over shared-memory arrays: the kernel stays inside the 32 KB
-// instruction cache (a fully unrolled register version spent most of its time in instruction fetch).
+// Bucket g exists twice, once per catalogue (the partition passes keep the catalogues apart).  Its
+// catalogue-1 members go into a bucketised shared-memory table: BJ_NB1 cells of 4 slots, filled through
+// one counter per cell, so a probe is a fixed 4-way compare (no open-addressing chains, no divergence).
+// A full cell (Poisson tail, ~6 % of the members) spills into BJ_NB2 secondary cells, those into a short
+// list.  The catalogue-0 members stream through registers and probe; every match is a hit record staged
+// in shared memory, partitioned there by halo-A range and written out in runs.
+// All loops over a bucket are rolled: the kernel stays inside the 32 KB instruction cache (a fully
+// unrolled version spent most of its time in instruction fetch).
 #define BJ_THREADS 512
 #define BJ_NB1 1536             // primary cells x 4 slots
 #define BJ_NB2 256              // secondary cells x 4 slots
 #define BJ_N3 32                // last-resort list
-#define BJ_SH 6144              // staging array: [BJ_SLACK][catalogue-0 members]; == 4 * BJ_NB1: the dead table is the sorted buffer
-#define BJ_SLACK 1536
-#define BJ_KPT 18               // keys per thread: cap2 <= BJ_THREADS * BJ_KPT
-#define BJ_BK 6                 // keys per thread and load batch
+#define BJ_SH 6144              // hits staged per bucket; == 4 * BJ_NB1: the dead table is the sorted buffer
+#define BJ_KPT 10               // keys per thread and catalogue: cap2 <= BJ_THREADS * BJ_KPT
+#define BJ_BK 5                 // keys per thread and load batch
 #define BJ_SMEM ((size_t) BJ_NB1 * 32 + (size_t) BJ_SH * 8 + (size_t) HIT_MAX_PARTS * 16)
 
-__global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ gcount, u64 cap2, KeyLayout L,
-								    u64 rmask, HitPlan hp, const u64 *__restrict__ hit_base,
+// cell hash of the pid bits that vary inside a bucket (the top bits of the mixed pid are the bucket number)
+__device__ __forceinline__ u32 bj_hash(u64 r) { return ((u32) r ^ (u32) (r >> 32)) * 0x9E3779B1u; }
+
+__global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ gcount, u64 n_buckets, u64 cap2,
+								    KeyLayout L, u64 rmask, HitPlan hp, const u64 *__restrict__ hit_base,
 								    const u32 *__restrict__ hit_cap, u32 *hit_cnt, u64 *__restrict__ hits_out,
 								    u64 *counters, u32 *overflow)
 {
 	extern __shared__ __align__(16) unsigned char bsm[];
 	u64 *t1 = reinterpret_cast<u64 *>(bsm);                              // [BJ_NB1 * 4] primary cells; later the hits sorted by partition
-	u64 *stage = t1 + BJ_NB1 * 4;                                        // [BJ_SH] catalogue-0 members, overwritten by the hits
+	u64 *stage = t1 + BJ_NB1 * 4;                                        // [BJ_SH] hits in discovery order
 	unsigned char *un = reinterpret_cast<unsigned char *>(stage + BJ_SH); // 16 KB used twice:
 	u64 *t2 = reinterpret_cast<u64 *>(un);                               //   build/probe: [BJ_NB2 * 4] secondary cells
 	u64 *t3 = t2 + BJ_NB2 * 4;                                           //                [BJ_N3]
@@ -280,47 +282,34 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + HIT_MAX_PARTS);        //                  [HIT_MAX_PARTS] counts, then write cursors
 	static_assert((size_t) BJ_NB2 * 32 + BJ_N3 * 8 + (BJ_NB1 + BJ_NB2) * 4 <= (size_t) HIT_MAX_PARTS * 16, "union overflow");
 	static_assert(BJ_SH == BJ_NB1 * 4 && BJ_KPT % BJ_BK == 0, "layout");
-	__shared__ u32 s_n0, s_n3, s_nhits, s_warpsum[BJ_THREADS / 32];
+	__shared__ u32 s_n3, s_nhits, s_warpsum[BJ_THREADS / 32];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const u64 g = blockIdx.x;
-	const u32 n = gcount[g];
-	if (n == 0 || (u64) n > cap2) return;                                // overflow was flagged by the partition pass already
-	const u64 *src = keys + g * cap2;
+	const u32 n0 = gcount[g], n1 = gcount[n_buckets + g];
+	if (n0 == 0 || n1 == 0 || (u64) n0 > cap2 || (u64) n1 > cap2) return;       // nothing to join / overflow flagged by the partition pass already
+	const u64 *src0 = keys + g * cap2, *src1 = keys + (n_buckets + g) * cap2;
 	for (int i = tid; i < BJ_NB1 + BJ_NB2; i += BJ_THREADS) cnt1[i] = 0; // cnt2 follows cnt1
-	if (tid == 0) { s_n0 = 0; s_n3 = 0; s_nhits = 0; }
-	u32 ovf = 0;                // overflow causes: 2 table full, 4 staging full, 8 hit region full
-	u64 *keys0 = stage + BJ_SLACK;
+	if (tid == 0) { s_n3 = 0; s_nhits = 0; }
+	u32 ovf = 0;                // overflow causes: 2 table full, 4 hit staging full, 8 hit region full
 	// build: the first loads fly while the counters are being cleared
 #pragma unroll 1
-	for (int bt = 0; bt < BJ_KPT / BJ_BK; bt++) {
+	for (u32 j0 = 0; j0 < n1; j0 += BJ_BK * BJ_THREADS) {
 		u64 key[BJ_BK];
 #pragma unroll
 		for (int i = 0; i < BJ_BK; i++) {
-			const u32 j = tid + (bt * BJ_BK + i) * BJ_THREADS;
-			key[i] = j < n ? ld_stream_u64(src + j) : 0ull;
+			const u32 j = j0 + i * BJ_THREADS + tid;
+			key[i] = j < n1 ? ld_stream_u64(src1 + j) : 0ull;
 		}
-		if (bt == 0) __syncthreads();
+		if (j0 == 0) __syncthreads();
 #pragma unroll
 		for (int i = 0; i < BJ_BK; i++) {
-			const bool valid = (tid + (bt * BJ_BK + i) * BJ_THREADS) < n;
-			const bool is1 = valid && key_snap(L, key[i]) != 0;
-			const u32 b0 = __ballot_sync(0xffffffffu, valid && !is1);
-			if (b0) {
-				u32 base = 0;
-				if (lane == 0) base = atomicAdd(&s_n0, (u32) __popc(b0));
-				base = __shfl_sync(0xffffffffu, base, 0);
-				if (valid && !is1) {
-					const u32 pos = base + __popc(b0 & lanemask_lt());
-					if (pos < BJ_SH - BJ_SLACK) keys0[pos] = key[i];
-				}
-			}
-			if (is1) {
-				const u64 hh = (key_pid(L, key[i]) & rmask) * 0x9E3779B97F4A7C15ull;
-				const u32 c1 = (u32) (((hh >> 32) * BJ_NB1) >> 32);
+			if (j0 + i * BJ_THREADS + tid < n1) {
+				const u32 hh = bj_hash(key_pid(L, key[i]) & rmask);
+				const u32 c1 = __umulhi(hh, BJ_NB1);
 				const u32 p1 = atomicAdd(&cnt1[c1], 1u);
 				if (p1 < 4) t1[c1 * 4 + p1] = key[i];
 				else {
-					const u32 c2 = (u32) (hh >> 20) & (BJ_NB2 - 1);
+					const u32 c2 = (hh >> 8) & (BJ_NB2 - 1);
 					const u32 p2 = atomicAdd(&cnt2[c2], 1u);
 					if (p2 < 4) t2[c2 * 4 + p2] = key[i];
 					else {
@@ -333,70 +322,78 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 		}
 	}
 	__syncthreads();
-	u32 n0 = s_n0;
-	if (n0 > BJ_SH - BJ_SLACK) { ovf |= 4u; n0 = BJ_SH - BJ_SLACK; }
 	const u32 n3 = s_n3 < BJ_N3 ? s_n3 : BJ_N3;
 	// probe: every match of a catalogue-0 member is one hit
 	const int tb = L.type_bits;
-	const u32 a_max = (hp.nbh << hp.log_hp) - 1u;                        // keeps the partition of a clobbered key in range after an overflow
+	const u64 pmask = ~((1ull << L.pid_shift) - 1ull);
+	const u64 lowmask = (1ull << L.snap_shift) - 1ull;                   // (halo, type) of a table entry
+	const u32 tmask = L.type_mask;
+	// (rolled, one body: the next two members of the thread are already in flight)
+	u64 ka = tid < n0 ? ld_stream_u64(src0 + tid) : 0ull;
+	u64 kb = tid + BJ_THREADS < n0 ? ld_stream_u64(src0 + tid + BJ_THREADS) : 0ull;
 #pragma unroll 1
-	for (u32 r0 = 0; r0 < n0; r0 += BJ_THREADS) {
-		const bool valid = r0 + tid < n0;
-		u64 recA = 0, pid = 0, hh = 0, first = 0, second = 0;
-		u32 m = 0;
-		// scans the cells of `pid`: the primary one, then (only if it was full) the secondary one, then the list;
-		// matches number `skip` and later are passed to f
-		auto scan = [&](u32 skip, auto f) {
-			const u64 *cell = t1 + (u32) (((hh >> 32) * BJ_NB1) >> 32) * 4;
-			u32 kc = cnt1[(u32) (((hh >> 32) * BJ_NB1) >> 32)], seen = 0;
-			int lvl = 0;
-			for (;;) {
-				const u32 kn = lvl < 2 ? (kc < 4 ? kc : 4) : kc;
-				for (u32 k = 0; k < kn; k++) {
-					const u64 e = cell[k];
-					if (key_pid(L, e) == pid) {
-						if (seen >= skip) f(recA | ((u64) key_halo(L, e) << (2 * tb)) | (u64) key_type(L, e));
-						seen++;
+	for (u32 j0 = 0; j0 < n0; j0 += BJ_THREADS) {
+		{
+			const u64 k0 = ka;
+			ka = kb;
+			kb = j0 + 2 * BJ_THREADS + tid < n0 ? ld_stream_u64(src0 + j0 + 2 * BJ_THREADS + tid) : 0ull;
+			u64 e0 = 0, e1 = 0;                                      // the first two matching table entries
+			u32 m = 0, hh = 0;
+#define BJ_CHK(e, ok)                                                                        \
+			if ((ok) && (((e) ^ k0) & pmask) == 0) { if (m == 0) e0 = (e); else if (m == 1) e1 = (e); m++; }
+			if (j0 + tid < n0) {
+				hh = bj_hash(key_pid(L, k0) & rmask);
+				const u32 c1 = __umulhi(hh, BJ_NB1);
+				const u32 kc = cnt1[c1];
+				const ulonglong2 ea = *reinterpret_cast<const ulonglong2 *>(t1 + c1 * 4), eb = *reinterpret_cast<const ulonglong2 *>(t1 + c1 * 4 + 2);
+				BJ_CHK(ea.x, kc > 0) BJ_CHK(ea.y, kc > 1) BJ_CHK(eb.x, kc > 2) BJ_CHK(eb.y, kc > 3)
+				if (kc > 4) {                                        // the cell was full: its overflow is in the secondary cell
+					const u32 c2 = (hh >> 8) & (BJ_NB2 - 1);
+					const u32 k2 = cnt2[c2];
+					const ulonglong2 fa = *reinterpret_cast<const ulonglong2 *>(t2 + c2 * 4), fb = *reinterpret_cast<const ulonglong2 *>(t2 + c2 * 4 + 2);
+					BJ_CHK(fa.x, k2 > 0) BJ_CHK(fa.y, k2 > 1) BJ_CHK(fb.x, k2 > 2) BJ_CHK(fb.y, k2 > 3)
+					if (k2 > 4)
+						for (u32 x = 0; x < n3; x++) { const u64 e = t3[x]; BJ_CHK(e, true) }
+				}
+			}
+#undef BJ_CHK
+			const u64 recA = ((u64) key_halo(L, k0) << hp.rec_a_shift) | ((u64) key_type(L, k0) << tb);
+			auto make_rec = [&](u64 e) { const u64 low = e & lowmask; return recA | ((low >> tb) << (2 * tb)) | (low & tmask); };
+			// first hits of the warp: one shared-memory atomic for all of them
+			const u32 ballot = __ballot_sync(0xffffffffu, m > 0);
+			if (ballot) {
+				u32 b = 0;
+				if (lane == 0) b = atomicAdd(&s_nhits, (u32) __popc(ballot));
+				b = __shfl_sync(0xffffffffu, b, 0);
+				if (m > 0) {
+					const u32 pos = b + __popc(ballot & lanemask_lt());
+					if (pos < BJ_SH) stage[pos] = make_rec(e0);
+				}
+			}
+			if (m > 1) {
+				u32 q = atomicAdd(&s_nhits, m - 1);
+				if (q < BJ_SH) stage[q] = make_rec(e1);
+				if (m > 2) {                                         // three or more memberships: rescan for the rest (rare)
+					u32 seen = 0;
+					auto rest = [&](const u64 *cell, u32 cnt) {
+						for (u32 k = 0; k < cnt; k++) {
+							const u64 e = cell[k];
+							if (((e ^ k0) & pmask) == 0) {
+								if (seen >= 2) { q++; if (q < BJ_SH) stage[q] = make_rec(e); }
+								seen++;
+							}
+						}
+					};
+					const u32 c1 = __umulhi(hh, BJ_NB1), c2 = (hh >> 8) & (BJ_NB2 - 1);
+					const u32 kc = cnt1[c1], k2 = cnt2[c2];
+					rest(t1 + c1 * 4, kc < 4 ? kc : 4);
+					if (kc > 4) {
+						rest(t2 + c2 * 4, k2 < 4 ? k2 : 4);
+						if (k2 > 4) rest(t3, n3);
 					}
 				}
-				if (lvl == 2 || kc <= 4) break;
-				if (lvl == 0) {
-					const u32 c2 = (u32) (hh >> 20) & (BJ_NB2 - 1);
-					cell = t2 + c2 * 4; kc = cnt2[c2]; lvl = 1;
-				} else { cell = t3; kc = n3; lvl = 2; }
-			}
-		};
-		if (valid) {
-			const u64 k0 = keys0[r0 + tid];
-			pid = key_pid(L, k0);
-			u32 A = key_halo(L, k0);
-			A = A < a_max ? A : a_max;
-			recA = ((u64) A << hp.rec_a_shift) | ((u64) key_type(L, k0) << tb);
-			hh = (pid & rmask) * 0x9E3779B97F4A7C15ull;
-			scan(0, [&](u64 rec) { if (m == 0) first = rec; else if (m == 1) second = rec; m++; });
-		}
-		__syncthreads();                                             // every member of this round is in registers: its slots may take hits
-		const u32 ballot = __ballot_sync(0xffffffffu, m > 0);
-		if (ballot) {
-			u32 b = 0;
-			if (lane == 0) b = atomicAdd(&s_nhits, (u32) __popc(ballot));
-			b = __shfl_sync(0xffffffffu, b, 0);
-			if (m > 0) {
-				const u32 pos = b + __popc(ballot & lanemask_lt());
-				if (pos < BJ_SH) stage[pos] = first;
 			}
 		}
-		if (m > 1) {
-			const u32 pos = atomicAdd(&s_nhits, m - 1);
-			if (pos < BJ_SH) stage[pos] = second;
-			if (m > 2) {                                                 // three or more memberships: rescan for the rest
-				u32 q = pos + 1;
-				scan(2, [&](u64 rec) { if (q < BJ_SH) stage[q] = rec; q++; });
-			}
-		}
-		// hits so far must stay behind the read frontier of the next round
-		__syncwarp();
-		if (*reinterpret_cast<volatile u32 *>(&s_nhits) > BJ_SLACK + r0 + BJ_THREADS && r0 + BJ_THREADS < n0) ovf |= 4u;
 	}
 	__syncthreads();                                                     // table and counters are dead from here on
 	u32 nh = s_nhits;
@@ -615,7 +612,7 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	if (ctx->cat[0].n_halos > (i64) HIT_MAX_PARTS * 8192) return false;
 	int tb = 0;
 	const i64 nmax = std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
-	while (((N >> tb) > 8000 || (nmax >> tb) > 4000) && tb < 20) tb++;   // final buckets of ~4-8 k keys, <= 4 k of either catalogue
+	while ((nmax >> tb) > 4000 && tb < 20) tb++;                    // final buckets of 2-4 k keys per catalogue
 	PartPlan P;
 	P.b1 = tb > 18 ? tb - 9 : (tb + 1) / 2;
 	P.b2 = tb - P.b1;
@@ -626,7 +623,8 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	P.shift1 = L.pid_shift + L.pid_bits - P.b1;
 	P.shift2 = P.shift1 - P.b2;
 	P.r1 = 8;
-	const double m1 = (double) N / (double) ((1ll << P.b1) * P.r1), m2 = (double) N / (double) (1ll << (P.b1 + P.b2));
+	// regions and buckets exist once per catalogue and are sized for the larger one
+	const double m1 = (double) nmax / (double) ((1ll << P.b1) * P.r1), m2 = (double) nmax / (double) (1ll << (P.b1 + P.b2));
 	P.cap1 = (u64) (m1 + 8.0 * sqrt(m1) + 4096.0);
 	P.cap1 = (P.cap1 + 1) & ~1ull;                                  // keep regions 16-byte aligned
 	P.cap2 = (u64) (m2 + 9.0 * sqrt(m2) + 64.0);
@@ -698,7 +696,8 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	cudaStream_t st = ctx->stream;
 	*fell_back = false;
 	const DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
-	const u64 nb1 = (1ull << P.b1) * P.r1, nb = 1ull << (P.b1 + P.b2);     // level-1 regions, final buckets
+	const u64 nbk = 1ull << (P.b1 + P.b2);                                 // buckets per catalogue
+	const u64 nb1 = 2 * (1ull << P.b1) * P.r1, nb = 2 * nbk;                // level-1 regions, final buckets (both catalogues)
 	const HitPlan hp = make_hit_plan(L, c0.n_halos);
 	const u64 hits_cap = 2ull * (u64) c0.n_tuples + (u64) (hp.slack + 2) * hp.nbh;
 	const u64 rec_cap = 16ull * (u64) (c0.n_halos + c1.n_halos) + (1ull << 20);
@@ -749,7 +748,7 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 		if (!attr) { CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BJ_SMEM)); attr = true; }
 		const int rb = L.pid_bits - P.b1 - P.b2;
 		const u64 rmask = rb >= 64 ? ~0ull : ((1ull << rb) - 1ull);
-		bucket_join_kernel<<<(unsigned) nb, BJ_THREADS, BJ_SMEM, st>>>(ctx->keys_b.as<u64>(), g2, P.cap2, L, rmask, hp, hit_base, hit_cap, hit_cnt,
+		bucket_join_kernel<<<(unsigned) nbk, BJ_THREADS, BJ_SMEM, st>>>(ctx->keys_b.as<u64>(), g2, nbk, P.cap2, L, rmask, hp, hit_base, hit_cap, hit_cnt,
 										ctx->keys_a.as<u64>(), counters, ovf);
 		CUDA_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
