@@ -45,17 +45,21 @@ template <int NB, bool PACK>
 __global__ void __launch_bounds__(PT_THREADS, 3) part_kernel(const u64 *__restrict__ in, const u32 *__restrict__ in_halo, const u8 *__restrict__ in_type,
 							     u64 n, u32 snap, u64 pid_base, KeyLayout L, PartPlan P, u64 *__restrict__ out,
 							     u32 *gcount_in /* level 2: counts of the level-1 regions */,
-							     u32 *gcount_out, u32 *overflow)
+							     u32 *gcount_out, u32 *overflow,
+							     u32 *t0 /* pass A, catalogue 0: tuples per hit partition (may be NULL) */, int log_hp, u32 nbh)
 {
 	extern __shared__ __align__(16) unsigned char psm[];
 	u64 *s_keys = reinterpret_cast<u64 *>(psm);                          // [PT_TILE]
 	i64 *s_dst = reinterpret_cast<i64 *>(s_keys + PT_TILE);              // [NB] global slot of a run minus its tile-local start
 	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + NB);                   // [NB]
 	u32 *s_start = s_cnt + NB;                                           // [NB]
+	u32 *s_hist = s_start + NB;                                          // [nbh] pass A, catalogue 0 only
 	__shared__ u32 s_warpsum[PT_THREADS / 32];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int BPT = NB / PT_THREADS > 0 ? NB / PT_THREADS : 1;       // buckets per thread in the scan
 	for (int i = tid; i < NB; i += PT_THREADS) s_cnt[i] = 0;
+	const bool hist = PACK && t0 != nullptr;
+	if (hist) for (u32 i = tid; i < nbh; i += PT_THREADS) s_hist[i] = 0;
 
 	u64 base, count;            // this tile = [base, base + count) of the input stream
 	u64 region = 0;             // level 2: which level-1 region
@@ -87,6 +91,19 @@ __global__ void __launch_bounds__(PT_THREADS, 3) part_kernel(const u64 *__restri
 			key[i] = ok ? __ldcs(src + idx) : 0ull;
 			ht[i] = ok ? __ldcs(in_halo + idx) : 0u;
 			rk[i] = ok ? (in_type ? (u32) __ldcs(in_type + idx) : 1u) : 0xFFFFFFFFu;     // type for now
+		}
+		if (hist) {
+			// catalogue-0 tuples per hit partition: the 32 consecutive tuples of a warp load normally sit in one halo range
+#pragma unroll
+			for (int i = 0; i < PT_ITEMS; i++) {
+				const bool ok = rk[i] != 0xFFFFFFFFu;
+				const u32 d = ht[i] >> log_hp;
+				const u32 d0 = __shfl_sync(0xffffffffu, d, 0);
+				const u32 okm = __ballot_sync(0xffffffffu, ok);
+				if (__all_sync(0xffffffffu, !ok || d == d0)) {
+					if (lane == 0 && okm && d0 < nbh) atomicAdd(&s_hist[d0], (u32) __popc(okm));
+				} else if (ok && d < nbh) atomicAdd(&s_hist[d], 1u);
+			}
 		}
 #pragma unroll
 		for (int i = 0; i < PT_ITEMS; i++) {
@@ -154,6 +171,11 @@ __global__ void __launch_bounds__(PT_THREADS, 3) part_kernel(const u64 *__restri
 		const u32 d = (u32) (k >> shift) & (NB - 1);
 		st_stream_u64(out + s_dst[d] + (i64) j, k);
 	}
+	if (hist)
+		for (u32 i = tid; i < nbh; i += PT_THREADS) {
+			const u32 c = s_hist[i];
+			if (c) atomicAdd(&t0[i], c);
+		}
 }
 
 // ---- hit regions ------------------------------------------------------------------------------
@@ -169,48 +191,6 @@ struct HitPlan {
 };
 #define HIT_MAX_PARTS 1024
 #define HIT_EMPTY 0xFFFFFFFFu
-
-// exact number of catalogue-0 tuples per hit partition (tuples of a halo are normally contiguous:
-// every thread run-length-compresses its 16 consecutive tuples before touching shared memory)
-#define HC_THREADS 256
-#define HC_ITEMS 16
-__global__ void __launch_bounds__(HC_THREADS) hit_count_kernel(const u32 *__restrict__ halo, u64 n, int log_hp, u32 nbh, int vec, u32 *__restrict__ t0)
-{
-	__shared__ u32 s_bin[HIT_MAX_PARTS];
-	for (u32 i = threadIdx.x; i < nbh; i += HC_THREADS) s_bin[i] = 0;
-	__syncthreads();
-	const u64 base = ((u64) blockIdx.x * HC_THREADS + threadIdx.x) * HC_ITEMS;
-	if (base < n) {
-		u32 h[HC_ITEMS];
-		if (vec && base + HC_ITEMS <= n) {
-			const uint4 *p = reinterpret_cast<const uint4 *>(halo + base);           // base is a multiple of 16 tuples = 64 B
-#pragma unroll
-			for (int q = 0; q < HC_ITEMS / 4; q++) {
-				const uint4 v = __ldg(p + q);
-				h[4 * q] = v.x; h[4 * q + 1] = v.y; h[4 * q + 2] = v.z; h[4 * q + 3] = v.w;
-			}
-		} else {
-#pragma unroll
-			for (int q = 0; q < HC_ITEMS; q++) h[q] = base + q < n ? halo[base + q] : 0xFFFFFFFFu;
-		}
-		u32 cur = 0xFFFFFFFFu, c = 0;
-#pragma unroll
-		for (int q = 0; q < HC_ITEMS; q++) {
-			const u32 d = h[q] == 0xFFFFFFFFu ? 0xFFFFFFFFu : h[q] >> log_hp;
-			if (d != cur) {
-				if (c && cur < nbh) atomicAdd(&s_bin[cur], c);
-				cur = d; c = 0;
-			}
-			c++;
-		}
-		if (c && cur < nbh) atomicAdd(&s_bin[cur], c);
-	}
-	__syncthreads();
-	for (u32 i = threadIdx.x; i < nbh; i += HC_THREADS) {
-		const u32 c = s_bin[i];
-		if (c) atomicAdd(&t0[i], c);
-	}
-}
 
 // block-wide exclusive scan of one u64 per thread (1024 threads)
 __device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64 *s_warp /* [32] */, u64 *total)
@@ -601,7 +581,7 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 	if (ovf) atomicOr(overflow, 16u);
 }
 
-static size_t part_smem(int nb) { return (size_t) PT_TILE * 8 + (size_t) nb * 16; }
+static size_t part_smem(int nb) { return (size_t) PT_TILE * 8 + (size_t) nb * 16 + (size_t) HIT_MAX_PARTS * 4; }
 
 // Is the partition path applicable, and with which bucket bits?
 bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out)
@@ -652,7 +632,7 @@ static HitPlan make_hit_plan(const KeyLayout &L, i64 H0)
 
 template <bool PACK>
 static int launch_part(metro_ctx *ctx, int bits, unsigned grid, const u64 *in, const u32 *ih, const u8 *it, u64 n, u32 snap, const KeyLayout &L,
-		       const PartPlan &P, u64 *out, u32 *gin, u32 *gout, u32 *ovf)
+		       const PartPlan &P, u64 *out, u32 *gin, u32 *gout, u32 *ovf, u32 *t0, const HitPlan &hp)
 {
 	cudaStream_t st = ctx->stream;
 	const size_t smem = part_smem(1 << bits);
@@ -660,7 +640,7 @@ static int launch_part(metro_ctx *ctx, int bits, unsigned grid, const u64 *in, c
 	case NB: {                                                                                                                  \
 		static bool attr = false;                                                                                           \
 		if (!attr) { CUDA_TRY(ctx, cudaFuncSetAttribute(part_kernel<NB, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr = true; } \
-		part_kernel<NB, PACK><<<grid, PT_THREADS, smem, st>>>(in, ih, it, n, snap, ctx->pid_base, L, P, out, gin, gout, ovf);   \
+		part_kernel<NB, PACK><<<grid, PT_THREADS, smem, st>>>(in, ih, it, n, snap, ctx->pid_base, L, P, out, gin, gout, ovf, t0, hp.log_hp, hp.nbh);   \
 		break;                                                                                                              \
 	}
 	switch (1 << bits) {
@@ -720,27 +700,21 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	u64 *counters = ctx->counters.as<u64>();
 	CUDA_TRY(ctx, cudaMemsetAsync(g1, 0, n32 * 4, st));
 	CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 8 * sizeof(u64), st));
-	// hit regions: exact catalogue-0 tuple count per halo range -> capacity and base
-	if (c0.n_tuples > 0) {
-		hit_count_kernel<<<(unsigned) div_up<i64>(c0.n_tuples, HC_THREADS * HC_ITEMS), HC_THREADS, 0, st>>>(c0.d_halo(), (u64) c0.n_tuples, hp.log_hp, hp.nbh,
-												    ((uintptr_t) c0.d_halo() & 15) == 0, t0);
-		CUDA_TRY(ctx, cudaGetLastError());
-		ctx->launches++;
-	}
-	hit_plan_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(t0, hp.nbh, hp.slack, hit_base, hit_cap);
-	CUDA_TRY(ctx, cudaGetLastError());
-	ctx->launches++;
 	// pass A: both catalogues (catalogue 0 first; the order inside a bucket is irrelevant)
 	for (int s = 0; s < 2; s++) {
 		const DevCatalogue &c = ctx->cat[s];
 		if (c.n_tuples == 0) continue;
 		if ((rc = launch_part<true>(ctx, P.b1, (unsigned) div_up<i64>(c.n_tuples, PT_TILE), c.d_pid(), c.d_halo(), c.d_type(), (u64) c.n_tuples, (u32) s, L, P,
-					    ctx->keys_a.as<u64>(), nullptr, g1, ovf))) return rc;
+					    ctx->keys_a.as<u64>(), nullptr, g1, ovf, s == 0 ? t0 : nullptr, hp))) return rc;
 	}
+	// hit regions: exact catalogue-0 tuple count per halo range (counted by pass A) -> capacity and base
+	hit_plan_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(t0, hp.nbh, hp.slack, hit_base, hit_cap);
+	CUDA_TRY(ctx, cudaGetLastError());
+	ctx->launches++;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
 	// pass B
 	if ((rc = launch_part<false>(ctx, P.b2, (unsigned) (nb1 * P.tiles1), ctx->keys_a.as<u64>(), nullptr, nullptr, 0, 0, L, P, ctx->keys_b.as<u64>(), g1, g2,
-				     ovf))) return rc;
+				     ovf, nullptr, hp))) return rc;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
 	// pass C
 	{
