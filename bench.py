@@ -5,9 +5,11 @@
     torchrun ... bench.py --gpus N ...                            # one rank per GPU (pid-range shards)
     python bench.py --impl reference ...                          # the reference's CPU path on the host cores
 
-A "step" is ONE pass of the hot path over one synthetic snapshot pair: pack -> radix sort ->
-run-length join -> pair-count reduce -> selection (forward + backward trees, mutual-best filter,
-orphan/token rule), device-resident tuples in, device-resident assignments out.
+A "step" is ONE pass of the hot path over one synthetic snapshot pair: pack + two hash-partition
+passes on the particle ID -> per-bucket shared-memory join (hit records out, partitioned by halo-A
+range) -> shared-memory pair count -> selection (forward + backward trees, mutual-best filter,
+orphan/token rule), device-resident tuples in, device-resident assignments out.  (Small pairs and
+adversarial inputs take the LSD radix sort + run-length join path instead; same results.)
 metric = bound particle IDs matched per second per pair = (N_A + N_B) / t_pair.
 
 Workload at N=1: configs[1] of BASELINE.json, the synthetic 1024^3 full-box pair (1e6 halos,
@@ -112,14 +114,13 @@ def measured_hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
-    """dram read+write bytes per onesweep launch from the committed ncu capture, if any."""
+def ncu_traffic():
+    """DRAM bytes per unit (key or hit) of each kernel from the committed ncu capture (profiles/traffic.json)."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            d = json.load(f)
-        return d.get("onesweep_dram_bytes_per_key")
+            return json.load(f)
     except Exception:
-        return None
+        return {}
 
 
 def pick_pid_bits(tuples_total_one_snapshot: int) -> int:
@@ -362,18 +363,52 @@ def run_ours(args, rank, world, local_rank):
     ms_per_step = ms_total / args.steps
     value = ids_glob / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (onesweep scatter pass): 8 B read + 8 B written per key
+    # ---- roofline: every streaming kernel of the path against the measured HBM peak; the headline object
+    # is the one that takes the most time.  Algorithmic bytes per launch:
+    #   partition path  A: 12 B (+1 with types) read + 8 B written per tuple   B: 8 + 8 per key
+    #                   C: 8 B per key read + 8 B per hit written               D: 8 B per hit read
+    #   LSD path        onesweep pass: 8 + 8 per key
     peak, peak_src = measured_hbm_peak()
-    avg_pass_ms = statistics.mean(pass_ms) if pass_ms else float("nan")
-    bytes_per_launch = 16.0 * ids_local
-    achieved = bytes_per_launch / (avg_pass_ms * 1e-3) / 1e9
-    per_key = ncu_traffic_per_launch()
-    roofline = {"bound": "hbm", "kernel": "onesweep_kernel<false,u32> (one LSD pass over the packed u64 keys)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                "traffic": per_key * ids_local if per_key else None,
-                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_pass_ms,
-                "launches_per_step": info["sort_passes"],
-                "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()}}
+    traffic = ncu_traffic()
+    path = int(t["path"])
+    hits_local = float(info["n_hits"]) / world            # n_hits is the global count; shards are statistically even
+    kernels = []
+    if path == 1:
+        per_step = [statistics.mean(pass_ms[i::4]) for i in range(4)]
+        tuple_in = 12.0 + (1.0 if prm.nptypes > 2 else 0.0)
+        spec_k = [("part_kernel<PACK> x2 (pass A: pack + level-1 partition, one launch per catalogue)", (tuple_in + 8.0) * ids_local, 2, "pass_a"),
+                  ("part_kernel (pass B: level-2 partition)", 16.0 * ids_local, 1, "pass_b"),
+                  ("bucket_join_kernel (pass C: shared-memory join, hit records out)", 8.0 * ids_local + 8.0 * hits_local, 1, "pass_c"),
+                  ("hit_reduce_kernel (pass D: shared-memory pair count)", 8.0 * hits_local, 1, "pass_d")]
+        for (name, nbytes, nl, key), ms in zip(spec_k, per_step):
+            ach = nbytes / (ms * 1e-3) / 1e9
+            kernels.append({"kernel": name, "ms_per_step": ms, "launches_per_step": nl, "algorithmic_bytes_per_step": nbytes,
+                            "achieved": ach, "frac": ach / peak, "traffic": traffic.get(key + "_dram_bytes_per_step")})
+    else:
+        avg_pass_ms = statistics.mean(pass_ms) if pass_ms else float("nan")
+        nbytes = 16.0 * ids_local
+        ach = nbytes / (avg_pass_ms * 1e-3) / 1e9
+        per_key = traffic.get("onesweep_dram_bytes_per_key")
+        kernels.append({"kernel": "onesweep_kernel (one LSD pass over the packed u64 keys)", "ms_per_step": avg_pass_ms * info["sort_passes"],
+                        "launches_per_step": info["sort_passes"], "algorithmic_bytes_per_step": nbytes * info["sort_passes"],
+                        "achieved": ach, "frac": ach / peak, "traffic": per_key * ids_local * info["sort_passes"] if per_key else None})
+    dom = max(kernels, key=lambda k: k["ms_per_step"])
+    # SURVEY 8(d) contract figure: bytes a textbook LSD sort + sort-reduce would move for this pair
+    P_sort = (info["pid_bits"] + 7) // 8
+    Pp = (2 * info["halo_bits"] + 7) // 8
+    contract_bytes = ids_local * (8 + 24 * P_sort) + ids_local * 12 + hits_local * 8 + hits_local * (16 + 16 * Pp)
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "peak_source": peak_src,
+                "traffic": (dom["traffic"] / dom["launches_per_step"]) if dom["traffic"] else None,
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_step"] / dom["launches_per_step"],
+                "avg_launch_ms": dom["ms_per_step"] / dom["launches_per_step"], "launches_per_step": dom["launches_per_step"],
+                "path": "partition join" if path == 1 else "LSD radix sort + run-length join",
+                "kernels": kernels,
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+                "survey_contract": {"bytes_per_pair": contract_bytes, "achieved": contract_bytes / (ms_per_step * 1e-3) / 1e9,
+                                    "frac": contract_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                                    "note": "SURVEY 8(d) algorithmic bytes of an LSD sort + sort-reduce pipeline / measured pair time; "
+                                            "the partition join moves fewer real bytes, so this can exceed 1"}}
 
     # ---- e2e: the user-facing call sequence with HOST buffers: upload both catalogues from pinned
     # memory, match, fetch the clean trees.
@@ -387,7 +422,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": ("synthetic 1024^3 full-box snapshot pair" if world == 1 else
                                     f"synthetic full-box snapshot pair sharded by particle-ID range over {world} GPUs"),
                        "halos_per_snapshot": H_glob, "bound_ids_per_snapshot": int(ids_glob / 2), "pid_bits": info["pid_bits"],
-                       "sort_passes": info["sort_passes"], "l2": "inputs (>= 8 GB of keys per pass) far exceed the 126 MB L2",
+                       "front_end": roofline["path"], "l2": "inputs (>= 8 GB of keys per pass) far exceed the 126 MB L2",
                        "params": "minPartCmp=10 minPartHalo=100 facOrphanSteps=100 maxOrphanSteps=15 (fullbox cfg)",
                        "n_hits": info["n_hits"], "n_pairs": info["n_pairs"], "n_trees": info["n_trees"],
                        "n_tokens": info["n_tokens"], "n_table_hits": info["n_table_hits"],
@@ -411,6 +446,9 @@ def run_ours(args, rank, world, local_rank):
 
 
 def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
+    """The user-facing call sequence with HOST buffers, every step: both catalogues go up from pinned host
+    memory in the layout an _particles file / locParts holds them (particle IDs grouped by halo + one offset
+    per halo: metro_catalogue_upload_csr), the pair is matched, the clean trees come back."""
     import numpy as np
     import torch
     import metrocpp_b200 as mb
@@ -423,21 +461,29 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
         halo = torch.empty(N, dtype=torch.int32, pin_memory=True)
         rc = eng.lib.metro_catalogue_fetch_tuples(eng.h, slot, pid.data_ptr(), halo.data_ptr(), None)
         eng._check(rc)
-        cats.append((halos, pid, halo))
-    h2d = sum(p.numel() * 8 + h.numel() * 4 + c.n_halos * (8 + 4 * prm.nptypes + 4 + 1) for c, p, h in cats)
+        # group the tuples by halo (file order of an AHF _particles file); preparation, not timed
+        h_dev = halo.to(dev)
+        h_sorted, order = torch.sort(h_dev, stable=True)
+        pid.copy_(pid.to(dev)[order])
+        counts = torch.bincount(h_sorted, minlength=H)
+        off = torch.zeros(H + 1, dtype=torch.int64, pin_memory=True)
+        off[1:].copy_(torch.cumsum(counts, 0))
+        del h_dev, h_sorted, order, counts
+        torch.cuda.empty_cache()
+        cats.append((halos, pid, off))
+    h2d = sum(p.numel() * 8 + o.numel() * 8 + c.n_halos * (8 + 4 * prm.nptypes + 4 + 4 + 1) for c, p, o in cats)
 
     def one():
-        for slot, (c, pid, halo) in enumerate(cats):
-            hc = mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, pid.numpy().view(np.uint64),
-                                  halo.numpy().view(np.uint32), None)
-            eng.upload(slot, prm, hc)
+        for slot, (c, pid, off) in enumerate(cats):
+            hc = mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, pid.numpy().view(np.uint64), None, None)
+            eng.upload(slot, prm, hc, halo_offset=off.numpy())
         info = eng.match_pair(prm)
         res = eng.fetch_result(info, raw=False)
         d2h = res.tree_main.nbytes + res.tree_orphan.nbytes + res.tree_off.nbytes + res.clean_prog.nbytes + \
             res.clean_ncommon.nbytes + res.token_halo.nbytes
-        return d2h
+        return d2h, info
 
-    one()                                                   # warm-up (allocations)
+    _, info0 = one()                                        # warm-up (allocations)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -445,7 +491,7 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(steps):
-        d2h = one()
+        d2h, info = one()
     ev1.record(stream)
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - t0
@@ -455,8 +501,9 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     return {"value": ids_glob / (ms / steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": ms / steps, "steps": steps,
-            "path": "metro_catalogue_upload x2 (pinned host SoA) -> metro_match_pair -> metro_result_fetch (clean trees)"}
+            "ms_per_step": ms / steps, "steps": steps, "n_trees": info["n_trees"],
+            "path": "metro_catalogue_upload_csr x2 (pinned host: u64 particle IDs grouped by halo + i64 offsets) -> "
+                    "metro_match_pair -> metro_result_fetch (clean trees)"}
 
 
 def main():

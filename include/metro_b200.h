@@ -125,6 +125,12 @@ const char *metro_version(void);
  * src/IOSettings.cpp:628-632) and the locHalos[slot] fill (:775-793): copies the host arrays
  * to HBM.  slot in {0,1}.  Caller keeps ownership of the host arrays. */
 int metro_catalogue_upload(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat);
+/* Same, for tuples grouped by halo the way an _particles file and locParts[slot][halo] hold them
+ * (src/global_vars.h:64, filled src/IOSettings.cpp:645-668): the tuples of halo h are
+ * pid[halo_offset[h] .. halo_offset[h+1]), halo_offset[0] = 0, halo_offset[n_halos] = n_tuples, non-decreasing;
+ * cat->halo is ignored (may be NULL) and the per-tuple halo index is rebuilt on the device: 8 instead of
+ * 12 bytes per tuple cross the bus. */
+int metro_catalogue_upload_csr(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat, const int64_t *halo_offset);
 /* Same, but the tuple arrays are already DEVICE pointers (zero copy; the context borrows them
  * until the next upload/shift of that slot).  Halo arrays stay host pointers. */
 int metro_catalogue_adopt_device(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat);

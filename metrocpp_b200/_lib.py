@@ -62,6 +62,7 @@ SYMBOLS = {
     "metro_version": (C.c_char_p, []),
     "metro_ctx_set_stream": (C.c_int, [_P, _P]),
     "metro_catalogue_upload": (C.c_int, [_P, C.c_int, C.POINTER(Params), C.POINTER(Catalogue)]),
+    "metro_catalogue_upload_csr": (C.c_int, [_P, C.c_int, C.POINTER(Params), C.POINTER(Catalogue), _P]),
     "metro_catalogue_adopt_device": (C.c_int, [_P, C.c_int, C.POINTER(Params), C.POINTER(Catalogue)]),
     "metro_match_pair": (C.c_int, [_P, C.POINTER(Params), C.POINTER(ResultInfo)]),
     "metro_result_fetch": (C.c_int, [_P, C.POINTER(ResultArrays)]),

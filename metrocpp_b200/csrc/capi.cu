@@ -157,36 +157,70 @@ static int upload_halos(metro_ctx *ctx, DevCatalogue &c, const metro_params *prm
 	return METRO_OK;
 }
 
-static int check_catalogue(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat)
+static int check_catalogue(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat, bool csr = false)
 {
 	int rc = check_params(ctx, prm);
 	if (rc) return rc;
 	if (slot < 0 || slot > 1 || !cat) { metro_set_error(ctx, "bad slot / NULL catalogue"); return METRO_ERR_INVALID; }
 	if (cat->n_halos < 0 || cat->n_tuples < 0 || cat->n_halos >= (1ll << 31)) { metro_set_error(ctx, "bad catalogue sizes"); return METRO_ERR_INVALID; }
 	if (cat->n_halos > 0 && (!cat->halo_id || !cat->npart)) { metro_set_error(ctx, "halo_id / npart is NULL"); return METRO_ERR_INVALID; }
-	if (cat->n_tuples > 0 && (!cat->pid || !cat->halo)) { metro_set_error(ctx, "pid / halo is NULL"); return METRO_ERR_INVALID; }
+	if (cat->n_tuples > 0 && (!cat->pid || (!csr && !cat->halo))) { metro_set_error(ctx, "pid / halo is NULL"); return METRO_ERR_INVALID; }
 	if (cat->n_tuples > 0 && cat->n_halos == 0) { metro_set_error(ctx, "tuples without halos"); return METRO_ERR_INVALID; }
 	return METRO_OK;
 }
 
-int metro_catalogue_upload(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat)
+// per-tuple halo index from CSR offsets: every thread owns 16 consecutive tuples, finds the halo of the
+// first one by binary search (offsets are L2 resident) and walks forward from there
+__global__ void __launch_bounds__(256) expand_halo_kernel(const i64 *__restrict__ off, i64 H, i64 N, u32 *__restrict__ halo)
 {
-	if (!ctx) return METRO_ERR_INVALID;
-	int rc = check_catalogue(ctx, slot, prm, cat);
-	if (rc) return rc;
+	const i64 base = ((i64) blockIdx.x * 256 + threadIdx.x) * 16;
+	if (base >= N) return;
+	i64 lo = 0, hi = H;                                                  // last h with off[h] <= base
+	while (hi - lo > 1) {
+		const i64 mid = (lo + hi) >> 1;
+		if (__ldg(off + mid) <= base) lo = mid; else hi = mid;
+	}
+	i64 h = lo, next = __ldg(off + h + 1);
+	u32 v[16];
+#pragma unroll
+	for (int q = 0; q < 16; q++) {
+		const i64 i = base + q;
+		while (i >= next && h + 1 < H) { h++; next = __ldg(off + h + 1); }
+		v[q] = (u32) h;
+	}
+	if (base + 16 <= N) {
+		uint4 *dst = reinterpret_cast<uint4 *>(halo + base);
+#pragma unroll
+		for (int q = 0; q < 4; q++) dst[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+	} else {
+		for (int q = 0; q < 16 && base + q < N; q++) halo[base + q] = v[q];
+	}
+}
+
+static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat, const int64_t *halo_offset)
+{
+	int rc;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	DevCatalogue &c = ctx->cat[slot];
 	c.valid = false; c.b_pid = nullptr; c.b_halo = nullptr; c.b_type = nullptr;
 	if ((rc = upload_halos(ctx, c, prm, cat))) return rc;
-	const i64 N = cat->n_tuples;
+	const i64 N = cat->n_tuples, H = cat->n_halos;
 	cudaStream_t st = ctx->stream;
 	if ((rc = dev_reserve(ctx, c.pid, (size_t) N * 8 + 8))) return rc;
-	if ((rc = dev_reserve(ctx, c.halo, (size_t) N * 4 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.halo, (size_t) N * 4 + 64))) return rc;
 	if (cat->type) { if ((rc = dev_reserve(ctx, c.type, (size_t) N + 8))) return rc; }
 	else dev_free(c.type);
 	if (N > 0) {
+		if (halo_offset) {
+			if (halo_offset[0] != 0 || halo_offset[H] != N) { metro_set_error(ctx, "halo_offset must run from 0 to n_tuples"); return METRO_ERR_INVALID; }
+			if ((rc = dev_reserve(ctx, ctx->scratch[79], (size_t) (H + 1) * 8))) return rc;
+			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scratch[79].p, halo_offset, (size_t) (H + 1) * 8, cudaMemcpyHostToDevice, st));
+			expand_halo_kernel<<<(unsigned) div_up<i64>(N, 256 * 16), 256, 0, st>>>(ctx->scratch[79].as<i64>(), H, N, c.halo.as<u32>());
+			CUDA_TRY(ctx, cudaGetLastError());
+		} else {
+			CUDA_TRY(ctx, cudaMemcpyAsync(c.halo.p, cat->halo, (size_t) N * 4, cudaMemcpyHostToDevice, st));
+		}
 		CUDA_TRY(ctx, cudaMemcpyAsync(c.pid.p, cat->pid, (size_t) N * 8, cudaMemcpyHostToDevice, st));
-		CUDA_TRY(ctx, cudaMemcpyAsync(c.halo.p, cat->halo, (size_t) N * 4, cudaMemcpyHostToDevice, st));
 		if (cat->type) CUDA_TRY(ctx, cudaMemcpyAsync(c.type.p, cat->type, (size_t) N, cudaMemcpyHostToDevice, st));
 	}
 	c.n_tuples = N;
@@ -195,6 +229,25 @@ int metro_catalogue_upload(metro_ctx *ctx, int slot, const metro_params *prm, co
 	ctx->nptypes = prm->nptypes;
 	ctx->res.valid = false;
 	return METRO_OK;
+}
+
+int metro_catalogue_upload_csr(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat, const int64_t *halo_offset)
+{
+	if (!ctx) return METRO_ERR_INVALID;
+	int rc = check_catalogue(ctx, slot, prm, cat, true);
+	if (rc) return rc;
+	if (!halo_offset) { metro_set_error(ctx, "halo_offset is NULL"); return METRO_ERR_INVALID; }
+	for (i64 h = 0; h < cat->n_halos; h++)
+		if (halo_offset[h + 1] < halo_offset[h]) { metro_set_error(ctx, "halo_offset decreases at halo %lld", (long long) h); return METRO_ERR_INVALID; }
+	return upload_tuples(ctx, slot, prm, cat, halo_offset);
+}
+
+int metro_catalogue_upload(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat)
+{
+	if (!ctx) return METRO_ERR_INVALID;
+	int rc = check_catalogue(ctx, slot, prm, cat);
+	if (rc) return rc;
+	return upload_tuples(ctx, slot, prm, cat, nullptr);
 }
 
 int metro_catalogue_adopt_device(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat)

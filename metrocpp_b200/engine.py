@@ -100,7 +100,8 @@ class MetroEngine:
             raise MetroError(rc, self.lib.metro_last_error(self.h).decode())
 
     # -- catalogues (locHalos[slot], locMapParts[slot]) ---------------------------------------
-    def upload(self, slot: int, prm: Params, cat: HostCatalogue, device_ptrs: tuple | None = None):
+    def upload(self, slot: int, prm: Params, cat: HostCatalogue, device_ptrs: tuple | None = None, halo_offset=None):
+        """halo_offset (int64[H+1]): tuples are grouped by halo (the locParts layout); cat.halo is then not sent."""
         T = prm.nptypes
         c = _lib.Catalogue()
         keep = []
@@ -121,9 +122,14 @@ class MetroEngine:
             self._check(self.lib.metro_catalogue_adopt_device(self.h, slot, C.byref(prm), C.byref(c)))
         else:
             c.pid = arr(cat.pid, np.uint64)
-            c.halo = arr(cat.halo, np.uint32)
             c.type = arr(cat.type, np.uint8) if cat.type is not None else None
-            self._check(self.lib.metro_catalogue_upload(self.h, slot, C.byref(prm), C.byref(c)))
+            if halo_offset is not None:
+                c.halo = None
+                off = arr(halo_offset, np.int64, (H + 1,))
+                self._check(self.lib.metro_catalogue_upload_csr(self.h, slot, C.byref(prm), C.byref(c), off))
+            else:
+                c.halo = arr(cat.halo, np.uint32)
+                self._check(self.lib.metro_catalogue_upload(self.h, slot, C.byref(prm), C.byref(c)))
         self.nptypes = T
 
     def catalogue_sizes(self, slot: int):

@@ -152,3 +152,35 @@ print("PATH_OK", eng.timings()["path"], res.info["n_hits"])
             env = dict(os.environ, EXPECT_PATH=expect, **env_extra)
             r = subprocess.run([sys.executable, "-c", code, nptypes], capture_output=True, text=True, cwd=root, env=env, timeout=600)
             assert r.returncode == 0 and "PATH_OK " + expect in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("nptypes", [2, 6])
+def test_csr_upload_rebuilds_the_halo_index(eng, nptypes):
+    """metro_catalogue_upload_csr (tuples grouped by halo + offsets, the locParts layout, with empty halos and a
+    ragged tail) must leave exactly the catalogue the per-tuple upload leaves, and match identically."""
+    prm = mb.make_params(nptypes=nptypes, max_orphan_steps=4)
+    spec = mb.SynthSpec(seed=5, n_halos=900, n_tuples=150_003, pid_bits=20, shard=0, n_shards=1)
+    cats = [mb.synth_pair_host(prm, spec, s) for s in range(2)]
+    grouped = []
+    for c in cats:
+        order = np.argsort(c.halo, kind="stable")
+        off = np.zeros(c.n_halos + 1, np.int64)
+        np.cumsum(np.bincount(c.halo, minlength=c.n_halos), out=off[1:])
+        grouped.append((mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, c.pid[order], c.halo[order],
+                                         None if c.type is None else c.type[order]), off))
+    for slot, (g, off) in enumerate(grouped):
+        eng.upload(slot, prm, g, halo_offset=off)
+        back = eng.fetch_catalogue(slot)
+        np.testing.assert_array_equal(back.halo, g.halo)
+        np.testing.assert_array_equal(back.pid, g.pid)
+    res_csr = eng.find_progenitors_and_clean(prm)
+    for slot, (g, _) in enumerate(grouped):
+        eng.upload(slot, prm, g)
+    res = eng.find_progenitors_and_clean(prm)
+    for k in ("tree_main", "tree_orphan", "tree_off", "clean_prog", "clean_ncommon", "token_halo"):
+        np.testing.assert_array_equal(getattr(res_csr, k), getattr(res, k), err_msg=k)
+    oprm = binding.Params(nptypes, prm.min_part_cmp, prm.min_part_halo, prm.fac_orphan_steps, prm.max_orphan_steps, 0)
+    compare_result_with_oracle(res_csr, binding.match_pair(oprm, to_oracle_catalogue(grouped[0][0]), to_oracle_catalogue(grouped[1][0])))
+    bad = grouped[0][1].copy(); bad[3] = bad[4] + 1
+    with pytest.raises(mb.MetroError):
+        eng.upload(0, prm, grouped[0][0], halo_offset=bad)
