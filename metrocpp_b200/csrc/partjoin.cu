@@ -499,14 +499,17 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 			const u32 tag = (u32) r[q] & tag_mask;
 			u32 *tg = s_tag + (size_t) a * WAYS;
 			int w = -1;
+			bool has_empty = true;                                       // ways only ever go from empty to taken
 			if (WAYS == 4) {
 				const uint4 t4 = *reinterpret_cast<const uint4 *>(tg);
 				w = t4.x == tag ? 0 : t4.y == tag ? 1 : t4.z == tag ? 2 : t4.w == tag ? 3 : -1;
+				has_empty = t4.w == HIT_EMPTY || t4.z == HIT_EMPTY || t4.y == HIT_EMPTY || t4.x == HIT_EMPTY;
 			} else if (WAYS == 2) {
 				const uint2 t2 = *reinterpret_cast<const uint2 *>(tg);
 				w = t2.x == tag ? 0 : t2.y == tag ? 1 : -1;
+				has_empty = t2.y == HIT_EMPTY || t2.x == HIT_EMPTY;
 			}
-			if (w < 0) {
+			if (w < 0 && has_empty) {
 				// first sight of this partner (or a race with its first sight): claim an empty way
 #pragma unroll
 				for (int x = 0; x < WAYS; x++) {
@@ -522,7 +525,7 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 			else {
 				u32 h = (u32) ((r[q] * 0x9E3779B97F4A7C15ull) >> 52) & (HR_OVF - 1);
 				int probe = 0;
-				for (; probe < HR_OVF_PROBES; probe++) {
+				for (; probe < HR_OVF_PROBES; probe++) {       // (left to the compiler: forcing this loop to stay rolled made the kernel 5x slower)
 					u64 cur = *reinterpret_cast<volatile u64 *>(s_okey + h);
 					if (cur == ~0ull) {
 						cur = atomicCAS((unsigned long long *) (s_okey + h), ~0ull, (unsigned long long) r[q]);
