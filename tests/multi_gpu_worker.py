@@ -47,6 +47,8 @@ def main():
     eng.upload(0, prm, shard(c0, lo, hi))
     eng.upload(1, prm, shard(c1, lo, hi))
     res = eng.find_progenitors_and_clean(prm)
+    if "METRO_EXPECT_PATH" in os.environ:
+        assert eng.timings()["path"] == int(os.environ["METRO_EXPECT_PATH"]), eng.timings()
     parts = [None] * world
     dist.all_gather_object(parts, {"tree_main": res.tree_main, "tree_orphan": res.tree_orphan, "tree_off": res.tree_off,
                                    "clean_prog": res.clean_prog, "clean_ncommon": res.clean_ncommon, "token": res.token_halo,

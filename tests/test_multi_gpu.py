@@ -17,11 +17,18 @@ def _ngpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,nptypes", [(2, 2), (2, 6), (4, 2)])
-def test_sharded_match_equals_oracle(world, nptypes):
+@pytest.mark.parametrize("world,nptypes,front_end", [(2, 2, "lsd"), (2, 6, "lsd"), (2, 2, "partition"), (2, 6, "partition"), (4, 2, "partition")])
+def test_sharded_match_equals_oracle(world, nptypes, front_end):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ)
+    if front_end == "partition":
+        env["METRO_PART_MIN_N"] = "20000"          # the shards are small: force the partition join front end
+        env["METRO_EXPECT_PATH"] = "1"
+    else:
+        env["METRO_FORCE_LSD"] = "1"
+        env["METRO_EXPECT_PATH"] = "0"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29700 + world + nptypes), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(nptypes)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
