@@ -1,0 +1,18 @@
+"""The partition-join front end on skewed / adversarial pairs and on the golden chains (GPU)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_partition_front_end_cases_vs_oracle():
+    env = dict(os.environ, METRO_PART_MIN_N="1000", METRO_DEBUG="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "partition_cases_worker.py")], capture_output=True, text=True,
+                       cwd=ROOT, env=env, timeout=900)
+    assert r.returncode == 0 and "PARTITION_CASES_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    # the two adversarial inputs took the fallback and said why
+    assert r.stderr.count("fell back to the LSD path") >= 2, r.stderr[-2000:]
