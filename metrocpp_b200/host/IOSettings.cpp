@@ -6,14 +6,20 @@
 #include "IOSettings.h"
 
 #include <dirent.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iomanip>
 #include <map>
+#include <memory>
+#include <thread>
 #include <unordered_map>
 
 #include "global_vars.h"
@@ -24,6 +30,29 @@ static std::string Strip(const std::string &s)
 	for (char c : s) if (c != ' ' && c != '\t' && c != '\r' && c != '\n') o.push_back(c);
 	return o;
 }
+
+// read-only view of a whole file (mmap: the page cache is parsed in place, no copy)
+struct FileView {
+	const char *p = nullptr;
+	size_t n = 0;
+	bool mapped = false;
+	bool Open(const std::string &path)
+	{
+		int fd = open(path.c_str(), O_RDONLY);
+		if (fd < 0) return false;
+		struct stat st;
+		if (fstat(fd, &st) != 0) { close(fd); return false; }
+		n = (size_t) st.st_size;
+		if (n == 0) { close(fd); p = ""; return true; }
+		void *m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+		close(fd);
+		if (m == MAP_FAILED) return false;
+		madvise(m, n, MADV_SEQUENTIAL);
+		p = (const char *) m; mapped = true;
+		return true;
+	}
+	~FileView() { if (mapped) munmap((void *) p, n); }
+};
 
 static bool ReadWholeFile(const std::string &path, std::string &out)
 {
@@ -211,6 +240,43 @@ void IOSettings::ReadHalos()
 	slotDirty[iUseCat] = true;
 }
 
+// One text line of an _particles file, tokenised: first and second unsigned number (kNone = absent).
+static const uint64_t kNone = ~0ull;
+
+// Parses [p, end) (whole lines) into a[]/b[]: one entry per line, blank lines included.
+static void TokeniseLines(const char *p, const char *end, uint64_t *a, uint64_t *b)
+{
+	size_t k = 0;
+	while (p < end) {
+		const char *q = SkipSpace(p, end);
+		uint64_t x = kNone, y = kNone;
+		if (q < end && *q >= '0' && *q <= '9') {
+			q = ScanU64(q, end, x);
+			q = SkipSpace(q, end);
+			if (q < end && *q >= '0' && *q <= '9') q = ScanU64(q, end, y);
+		}
+		a[k] = x; b[k] = y; k++;
+		p = NextLine(q, end);
+	}
+}
+
+static size_t CountLines(const char *p, const char *end)
+{
+	size_t n = 0;
+	while (p < end) {
+		const char *nl = (const char *) memchr(p, '\n', (size_t) (end - p));
+		n++;
+		if (!nl) break;
+		p = nl + 1;
+	}
+	return n;
+}
+
+// AHF _particles reader (reference src/IOSettings.cpp:599-689: "nHalos", then per halo "nPart haloID" and
+// nPart lines "pid [type]").  The grammar is sequential (a header is only recognisable by position), so the
+// file is tokenised in parallel on all host cores (one entry per line), the header chain is walked serially
+// (one step per halo), and the tuples are copied out in parallel.  Tuples come out grouped by halo; when the
+// halos appear in catalogue order (the normal case) the per-halo offsets are kept for the CSR upload.
 void IOSettings::ReadParticles()
 {
 	TupleSoA &T = locTuples[iUseCat];
@@ -219,19 +285,61 @@ void IOSettings::ReadParticles()
 	std::unordered_map<uint64_t, uint32_t> byId;                       // only consulted when the order differs
 	size_t iHalo = 0;
 	size_t dropped = 0;
+	bool inOrder = true;
+	const bool verbose = getenv("METRO_DEBUG") != nullptr;
+	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double tRead = 0, tTok = 0, tChain = 0, tCopy = 0;
+	size_t bytes = 0;
+	int64_t lastIdx = -1;
+	struct Span { int64_t idx; size_t line, count, out; };
+	unsigned nThreads = std::thread::hardware_concurrency();
+	const char *forced = getenv("METRO_INGEST_THREADS");               // tests: force the chunked path on small files
+	if (forced && atoi(forced) > 0) nThreads = (unsigned) atoi(forced);
+	if (nThreads == 0) nThreads = 1;
+	if (nThreads > 64) nThreads = 64;
 	for (const std::string &path : partFiles[iNumCat]) {
-		std::string buf;
-		if (!ReadWholeFile(path, buf)) Fatal("file " + path + " not found");
+		FileView buf;
+		double t0 = now();
+		if (!buf.Open(path)) Fatal("file " + path + " not found");
 		if (locTask == 0) printf("Reading particle file: %s\n", path.c_str());
-		const char *p = buf.data(), *end = p + buf.size();
-		T.pid.reserve(T.pid.size() + buf.size() / 12);
-		while (p < end) {
-			uint64_t nFileHalos = 0;
-			p = NextLine(ScanU64(p, end, nFileHalos), end);            // line 1: halos in this block (src/IOSettings.cpp:603-606)
-			for (uint64_t fh = 0; fh < nFileHalos && p < end; fh++) {
-				uint64_t nPartHalo = 0, haloID = 0;
-				p = ScanU64(p, end, nPartHalo);
-				p = NextLine(ScanU64(p, end, haloID), end);            // "nPart haloID" (:610)
+		const char *base = buf.p, *end = base + buf.n;
+		bytes += buf.n;
+		double t1 = now();
+		tRead += t1 - t0;
+		// chunks of whole lines
+		const unsigned nt = (buf.n < (1u << 20) && !forced) ? 1u : nThreads;
+		std::vector<const char *> cut(nt + 1, end);
+		cut[0] = base;
+		for (unsigned t = 1; t < nt; t++) {
+			const char *c = base + buf.n / nt * t;
+			cut[t] = c <= cut[t - 1] ? cut[t - 1] : NextLine(c, end);
+		}
+		std::vector<size_t> lineOff(nt + 1, 0);
+		{
+			std::vector<std::thread> th;
+			for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t] { lineOff[t + 1] = CountLines(cut[t], cut[t + 1]); });
+			for (auto &x : th) x.join();
+		}
+		for (unsigned t = 0; t < nt; t++) lineOff[t + 1] += lineOff[t];
+		const size_t nLines = lineOff[nt];
+		std::unique_ptr<uint64_t[]> A(new uint64_t[nLines + 1]), B(new uint64_t[nLines + 1]);     // uninitialised: every entry is written below
+		{
+			std::vector<std::thread> th;
+			for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t] { TokeniseLines(cut[t], cut[t + 1], A.get() + lineOff[t], B.get() + lineOff[t]); });
+			for (auto &x : th) x.join();
+		}
+		double t2 = now();
+		tTok += t2 - t1;
+		// header chain
+		std::vector<Span> spans;
+		size_t outPos = T.pid.size(), k = 0;
+		while (k < nLines) {
+			while (k < nLines && A[k] == kNone) k++;                   // blank lines between blocks
+			if (k >= nLines) break;
+			const uint64_t nFileHalos = A[k++];                        // line 1 of a block: halos in it (src/IOSettings.cpp:603-606)
+			for (uint64_t fh = 0; fh < nFileHalos && k < nLines; fh++) {
+				const uint64_t nPartHalo = A[k] == kNone ? 0 : A[k], haloID = B[k] == kNone ? 0 : B[k];   // "nPart haloID" (:610)
+				k++;
 				int64_t idx = -1;
 				if (iHalo < H.size() && H[iHalo].ID == haloID) idx = (int64_t) iHalo++;
 				else {
@@ -239,20 +347,63 @@ void IOSettings::ReadParticles()
 					auto it = byId.find(haloID);
 					if (it != byId.end()) idx = it->second;
 				}
-				for (uint64_t k = 0; k < nPartHalo && p < end; k++) {
-					uint64_t pid = 0, type = 1;
-					p = ScanU64(p, end, pid);
-					if (!noPType) { p = ScanU64(p, end, type); if (type >= (uint64_t) nPTypes) Fatal("particle type >= nPTypes in " + path); }
-					p = NextLine(p, end);
-					if (idx < 0) { dropped++; continue; }
-					T.pid.push_back(pid);
-					T.halo.push_back((uint32_t) idx);
-					T.type.push_back((uint8_t) type);
+				const size_t cnt = (size_t) std::min<uint64_t>(nPartHalo, nLines - k);
+				if (idx < 0) dropped += cnt;
+				else {
+					if (idx <= lastIdx) inOrder = false;
+					lastIdx = idx;
+					spans.push_back({idx, k, cnt, outPos});
+					outPos += cnt;
 				}
+				k += cnt;
 			}
-			p = SkipSpace(p, end);
-			while (p < end && *p == '\n') p = SkipSpace(p + 1, end);
 		}
+		double t3 = now();
+		tChain += t3 - t2;
+		// copy out
+		T.pid.resize(outPos); T.halo.resize(outPos); T.type.resize(outPos);
+		{
+			std::vector<std::thread> th;
+			// equal shares of the output range (halo sizes follow a power law: equal shares of spans would not balance)
+			const size_t first = spans.empty() ? 0 : spans[0].out, total = outPos - first;
+			for (unsigned t = 0; t < nt; t++)
+				th.emplace_back([&, t] {
+					const size_t lo = first + total * t / nt, hi = first + total * (t + 1) / nt;
+					// first span that ends after lo
+					size_t si = (size_t) (std::upper_bound(spans.begin(), spans.end(), lo, [](size_t v, const Span &sp) { return v < sp.out + sp.count; }) - spans.begin());
+					for (; si < spans.size() && spans[si].out < hi; si++) {
+						const Span &sp = spans[si];
+						const size_t i0 = sp.out < lo ? lo - sp.out : 0, i1 = std::min(sp.count, hi - sp.out);
+						for (size_t i = i0; i < i1; i++) {
+							const uint64_t pid = A[sp.line + i], ty = B[sp.line + i];
+							T.pid[sp.out + i] = pid == kNone ? 0 : pid;
+							T.halo[sp.out + i] = (uint32_t) sp.idx;
+							T.type[sp.out + i] = noPType ? 1 : (uint8_t) (ty == kNone ? 0 : std::min<uint64_t>(ty, 255));
+						}
+					}
+				});
+			for (auto &x : th) x.join();
+		}
+		if (!noPType)
+			for (const Span &sp : spans)
+				for (size_t i = 0; i < sp.count; i++)
+					if (T.type[sp.out + i] >= nPTypes) Fatal("particle type >= nPTypes in " + path);
+		if (inOrder) {
+			if (T.haloOffset.empty()) T.haloOffset.assign(H.size() + 1, -1);
+			for (const Span &sp : spans) T.haloOffset[sp.idx] = (int64_t) sp.out;
+		}
+		tCopy += now() - t3;
+	}
+	if (verbose)
+		fprintf(stderr, "[metro] _particles ingest: %.1f MB, %zu tuples, %u threads: read %.3f s, tokenise %.3f s, header chain %.3f s, copy-out %.3f s\n",
+			bytes / 1e6, T.pid.size(), nThreads, tRead, tTok, tChain, tCopy);
+	if (inOrder && !H.empty()) {
+		// halos without a block own an empty range; ranges are contiguous because spans were appended in order
+		if (T.haloOffset.empty()) T.haloOffset.assign(H.size() + 1, -1);
+		T.haloOffset[H.size()] = (int64_t) T.pid.size();
+		for (size_t h = H.size(); h-- > 0;) if (T.haloOffset[h] < 0) T.haloOffset[h] = T.haloOffset[h + 1];
+	} else {
+		T.haloOffset.clear();
 	}
 	if (dropped) fprintf(stderr, "WARNING: %zu particle lines belong to halo IDs that are not in the halo catalogue; ignored\n", dropped);
 	slotDirty[iUseCat] = true;

@@ -47,7 +47,9 @@ static void UploadSlot(int slot)
 	c.pid = T.pid.data(); c.halo = T.halo.data();
 	c.type = noPType ? nullptr : T.type.data();
 	metro_params prm = CurrentParams();
-	Check(metro_catalogue_upload(gpuCtx, slot, &prm, &c), "catalogue upload");
+	// tuples grouped by halo in catalogue order (the normal _particles layout): 8 instead of 12 bytes per tuple go up
+	if (T.haloOffset.size() == n + 1 && n > 0) Check(metro_catalogue_upload_csr(gpuCtx, slot, &prm, &c, T.haloOffset.data()), "catalogue upload");
+	else Check(metro_catalogue_upload(gpuCtx, slot, &prm, &c), "catalogue upload");
 	slotDirty[slot] = false;
 }
 

@@ -16,7 +16,12 @@ struct TupleSoA {                      // one catalogue's "lines of the _particl
 	std::vector<uint64_t> pid;
 	std::vector<uint32_t> halo;    // index into locHalos[i]
 	std::vector<uint8_t> type;
-	void clear() { pid.clear(); halo.clear(); type.clear(); pid.shrink_to_fit(); halo.shrink_to_fit(); type.shrink_to_fit(); }
+	std::vector<int64_t> haloOffset;   // [nHalos + 1] when the tuples are grouped by halo in catalogue order (else empty)
+	void clear()
+	{
+		pid.clear(); halo.clear(); type.clear(); haloOffset.clear();
+		pid.shrink_to_fit(); halo.shrink_to_fit(); type.shrink_to_fit(); haloOffset.shrink_to_fit();
+	}
 };
 
 extern int locTask, totTask;

@@ -61,6 +61,19 @@ def test_ahf_ingest_matches_python_reader(tmp_path, fullbox_names):
         assert int(kv["halo_ck"]) == fnv(int(i) + int(n) for i, n in zip(s.halo_id, s.npart))
 
 
+def test_parallel_ingest_equals_serial(tmp_path):
+    """The chunked multi-thread _particles parser (one entry per line, serial header chain, parallel copy-out)
+    gives the same tuples as one thread, whatever the number of chunks."""
+    snaps, params, _ = golden_io.load("fullbox_chain20")
+    cfg, _ = write_case(str(tmp_path), snaps[:3], params, "gather", True)
+    outs = []
+    for nt in ("1", "3", "7", "64"):
+        r = subprocess.run([BIN, "--parse-only", cfg], capture_output=True, text=True, env=dict(os.environ, METRO_INGEST_THREADS=nt))
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append([ln for ln in r.stdout.splitlines() if ln.startswith("PARSED")])
+    assert len(outs[0]) == 3 and all(o == outs[0] for o in outs[1:])
+
+
 def test_missing_input_fails_loudly(tmp_path):
     cfg = tmp_path / "c.cfg"
     cfg.write_text("inputFormat = AHF\nhaloSuffix = AHF_halos\npartSuffix = AHF_particles\nhaloPrefix = snapshot_\n"
