@@ -186,6 +186,8 @@ struct HitPlan {
 	int rec_a_shift;            // halo_bits + 2 type_bits
 	int log_hp;                 // halos per hit partition (log2)
 	int ways;                   // (tag,count) slots per halo in pass D
+	int log_hs;                 // halos one pass-D block counts (<= log_hp): a partition is read 2^(log_hp-log_hs) times,
+	                            // each block keeping the hits of its sub-range (many halos per GPU, e.g. a pid shard of a big box)
 	u32 nbh;                    // hit partitions
 	u32 slack;                  // fixed part of a region's capacity
 };
@@ -438,6 +440,7 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 #define HR_OVF 4096             // entries of the per-block hash table for pairs beyond a halo's WAYS slots
 #define HR_OVF_PROBES 32
 #define HR_MAX_UNITS (2 * HIT_MAX_PARTS)   // sum of ceil(c_d / (3 mean)) <= nbh + nbh / 3
+#define HR_MAX_SUB_LOG 4                   // a partition holds up to 2^4 sub-ranges of 2048 halos: 32 M catalogue-0 halos per GPU
 
 __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__restrict__ hit_cnt, u32 nbh, uint4 *__restrict__ units, u32 *n_units)
 {
@@ -449,21 +452,34 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__r
 	u64 slice_max = 3 * (total / nbh) + 1;                          // only partitions well above the mean are split
 	if (slice_max < 65536) slice_max = 65536;
 	const u64 nsl = c ? (c + slice_max - 1) / slice_max : 0;
+	// longest units first (blocks are scheduled in index order: a heavy unit started last would be the tail):
+	// rank of this partition by its per-unit size, ties by index
+	__shared__ u32 s_size[HIT_MAX_PARTS];
+	const u32 usz = nsl ? (u32) ((c + nsl - 1) / nsl) : 0u;
+	s_size[d] = usz;
+	__syncthreads();
+	u32 before_units = 0;
+	for (u32 e = 0; e < nbh; e++) {
+		const u32 z = s_size[e];
+		if (z > usz || (z == usz && e < d)) before_units += z ? (u32) ((hit_cnt[e * CSTRIDE] + (u64) slice_max - 1) / slice_max) : 0u;
+	}
 	u64 tot_units;
-	const u64 off = block_excl_scan_u64(nsl, s_warp, &tot_units);
-	for (u64 s = 0; s < nsl; s++) units[off + s] = make_uint4(d, (u32) s, (u32) nsl, 0u);
+	block_excl_scan_u64(nsl, s_warp, &tot_units);
+	if (d < nbh) for (u64 s = 0; s < nsl; s++) units[before_units + s] = make_uint4(d, (u32) s, (u32) nsl, 0u);
 	if (d == 0) *n_units = (u32) tot_units;
 }
 
-template <int WAYS>
+template <int WAYS, bool SUB>
 __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__restrict__ hits, const u64 *__restrict__ hit_base,
 								 const u32 *__restrict__ hit_cnt, const uint4 *__restrict__ units,
 								 const u32 *__restrict__ n_units, HitPlan hp, u64 *__restrict__ rec_key,
 								 u32 *__restrict__ rec_cnt, u64 rec_cap, u64 *counters, u32 *overflow)
 {
-	if (blockIdx.x >= *n_units) return;
+	const int sub_log = SUB ? hp.log_hp - hp.log_hs : 0;
+	const u32 sub = SUB ? blockIdx.x & ((1u << sub_log) - 1u) : 0u;
+	if ((blockIdx.x >> sub_log) >= *n_units) return;
 	extern __shared__ __align__(16) unsigned char hsm[];
-	const u32 HP = 1u << hp.log_hp;
+	const u32 HP = 1u << hp.log_hs;                                      // halos counted by this block
 	u32 *s_tag = reinterpret_cast<u32 *>(hsm);                           // [HP * WAYS]
 	u32 *s_count = s_tag + (size_t) HP * WAYS;                           // [HP * WAYS]
 	u64 *s_okey = reinterpret_cast<u64 *>(s_count + (size_t) HP * WAYS); // [HR_OVF] pairs whose halo ran out of ways: open addressing on the record
@@ -471,7 +487,7 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 	__shared__ u32 s_warpsum[HR_THREADS / 32];
 	__shared__ u64 s_base;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint4 u = units[blockIdx.x];
+	const uint4 u = units[blockIdx.x >> sub_log];
 	const u32 d = u.x;
 	const u64 cnt = hit_cnt[d * CSTRIDE];
 	u64 per = (cnt + u.z - 1) / u.z;
@@ -495,7 +511,9 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 #pragma unroll
 		for (int q = 0; q < UNR; q++) {
 			if (r[q] == ~0ull) continue;
-			const u32 a = (u32) (r[q] >> hp.rec_a_shift) & (HP - 1u);
+			const u32 ap = (u32) (r[q] >> hp.rec_a_shift);                  // halo; its low log_hp bits index the partition
+			if (SUB && ((ap >> hp.log_hs) & ((1u << sub_log) - 1u)) != sub) continue;
+			const u32 a = ap & (HP - 1u);
 			const u32 tag = (u32) r[q] & tag_mask;
 			u32 *tg = s_tag + (size_t) a * WAYS;
 			int w = -1;
@@ -568,7 +586,7 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 		for (u32 i = tid; i < HP * WAYS; i += HR_THREADS) {
 			const u32 t = s_tag[i];
 			if (t != HIT_EMPTY) {
-				rec_key[o] = ((u64) (d * HP + i / WAYS) << hp.rec_a_shift) | (u64) t;
+				rec_key[o] = ((u64) ((d << hp.log_hp) + (sub << hp.log_hs) + i / WAYS) << hp.rec_a_shift) | (u64) t;
 				rec_cnt[o] = s_count[i];
 				o++;
 			}
@@ -592,7 +610,7 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	static const i64 min_n = getenv("METRO_PART_MIN_N") ? atoll(getenv("METRO_PART_MIN_N")) : (1ll << 23);
 	if (N < min_n || L.pid_bits < 16) return false;                 // small pairs: the LSD path is fine
 	if (L.halo_bits + 2 * L.type_bits > 31) return false;           // the pass-D way tag (B, tA, tB) is 31 bits
-	if (ctx->cat[0].n_halos > (i64) HIT_MAX_PARTS * 8192) return false;
+	if (ctx->cat[0].n_halos > ((i64) HIT_MAX_PARTS << (11 + HR_MAX_SUB_LOG))) return false;
 	int tb = 0;
 	const i64 nmax = std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
 	while ((nmax >> tb) > 4000 && tb < 20) tb++;                    // final buckets of 2-4 k keys per catalogue
@@ -624,10 +642,10 @@ static HitPlan make_hit_plan(const KeyLayout &L, i64 H0)
 {
 	HitPlan hp;
 	hp.rec_a_shift = L.halo_bits + 2 * L.type_bits;
-	hp.ways = 4; hp.log_hp = 11;                                    // 2048 halos x 4 ways x 8 B = 64 KB: two pass-D blocks per SM
+	hp.ways = 4; hp.log_hs = 11;                                    // 2048 halos x 4 ways x 8 B = 64 KB: two pass-D blocks per SM
+	hp.log_hp = 11;
 	auto parts = [&](int lg) { return (u64) div_up<i64>(std::max<i64>(H0, 1), 1ll << lg); };
-	if (parts(hp.log_hp) > HIT_MAX_PARTS) { hp.ways = 2; hp.log_hp = 12; }
-	while (parts(hp.log_hp) > HIT_MAX_PARTS && hp.log_hp < 13) hp.log_hp++;
+	while (parts(hp.log_hp) > HIT_MAX_PARTS && hp.log_hp < 11 + HR_MAX_SUB_LOG) hp.log_hp++;
 	hp.nbh = (u32) parts(hp.log_hp);
 	hp.slack = 2048;
 	return hp;
@@ -656,14 +674,14 @@ static int launch_part(metro_ctx *ctx, int bits, unsigned grid, const u64 *in, c
 	return METRO_OK;
 }
 
-template <int WAYS>
+template <int WAYS, bool SUB>
 static int launch_reduce(metro_ctx *ctx, const HitPlan &hp, const u64 *hits, const u64 *hit_base, const u32 *hit_cnt, const uint4 *units, const u32 *n_units,
 			 u64 *rec_key, u32 *rec_cnt, u64 rec_cap, u32 *ovf)
 {
-	const size_t smem = ((size_t) WAYS << hp.log_hp) * 8 + (size_t) HR_OVF * 12;
+	const size_t smem = ((size_t) WAYS << hp.log_hs) * 8 + (size_t) HR_OVF * 12;
 	static size_t attr = 0;
-	if (attr < smem) { CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<WAYS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr = smem; }
-	hit_reduce_kernel<WAYS><<<HR_MAX_UNITS, HR_THREADS, smem, ctx->stream>>>(hits, hit_base, hit_cnt, units, n_units, hp, rec_key, rec_cnt, rec_cap,
+	if (attr < smem) { CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<WAYS, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr = smem; }
+	hit_reduce_kernel<WAYS, SUB><<<HR_MAX_UNITS << (hp.log_hp - hp.log_hs), HR_THREADS, smem, ctx->stream>>>(hits, hit_base, hit_cnt, units, n_units, hp, rec_key, rec_cnt, rec_cap,
 										   ctx->counters.as<u64>(), ovf);
 	CUDA_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
@@ -735,8 +753,8 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	hit_units_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(hit_cnt, hp.nbh, units, n_units);
 	CUDA_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
-	if (hp.ways == 4) rc = launch_reduce<4>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
-	else rc = launch_reduce<2>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
+	if (hp.log_hp == hp.log_hs) rc = launch_reduce<4, false>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
+	else rc = launch_reduce<4, true>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
 	if (rc) return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 60, ovf, 4, cudaMemcpyDeviceToHost, st));
