@@ -71,7 +71,7 @@ __global__ void rec_key_kernel(const u64 *rec, i64 n, HitLayout hl, const u32 *r
 	if (i >= n) return;
 	u32 A, B, tA, tB;
 	hit_decode(hl, rec[i], A, B, tA, tB);
-	key[i] = ((u64) A << 32) | rank1[B];
+	key[i] = ((u64) A << hl.halo_bits) | rank1[B];      // 2 halo_bits wide: one radix pass per 8 bits of it
 	val[i] = (u32) i;
 }
 
@@ -118,10 +118,10 @@ __global__ void pair_compact_kernel(const u32 *flag, const u32 *scan, i64 n, int
 __global__ void count_by_kernel(const u32 *main, i64 n, u32 *cnt) { TID; if (i < n) atomicAdd(&cnt[main[i]], 1u); }
 
 // backward ordering key: (B, idRank0[A])
-__global__ void bwd_key_kernel(const u32 *kA, const u32 *kB, const u32 *rank0, i64 n, u64 *key, u32 *val)
+__global__ void bwd_key_kernel(const u32 *kA, const u32 *kB, const u32 *rank0, int hbits, i64 n, u64 *key, u32 *val)
 {
 	TID;
-	if (i < n) { key[i] = ((u64) kB[i] << 32) | rank0[kA[i]]; val[i] = (u32) i; }
+	if (i < n) { key[i] = ((u64) kB[i] << hbits) | rank0[kA[i]]; val[i] = (u32) i; }
 }
 
 __global__ void gather_dir_kernel(const u32 *perm, i64 n, int T, const u32 *src_main, const u32 *src_other, const i32 *src_nc,
@@ -151,6 +151,63 @@ __global__ void merit_key_kernel(const u32 *m_main, const u32 *m_other, const i3
 	merit[i] = mb;
 	key[i] = ((u64) a << 32) | low;
 	val[i] = (u32) i;
+}
+
+// Segmented merit sort: the candidates of one halo (a few, rarely hundreds) are ordered by (descending
+// merit, position) without touching the other segments.  Same order as the stable radix sort on
+// (halo, ~merit) it replaces, at a fraction of the passes.  One warp per segment: up to 32 candidates
+// are sorted in registers by a bitonic network; longer segments are queued for seg_sort_long_kernel.
+__global__ void __launch_bounds__(256) seg_sort_warp_kernel(const u64 *__restrict__ key, const u32 *__restrict__ segoff, const u32 *__restrict__ segcnt,
+							     i64 H, u32 *__restrict__ sidx, u32 *long_list, u32 *n_long)
+{
+	const i64 a = ((i64) blockIdx.x * 256 + threadIdx.x) >> 5;
+	const u32 lane = threadIdx.x & 31;
+	if (a >= H) return;
+	const u32 L = segcnt[a], off = segoff[a];
+	if (L == 0) return;
+	if (L == 1) { if (lane == 0) sidx[off] = off; return; }
+	if (L > 32) { if (lane == 0) long_list[atomicAdd(n_long, 1u)] = (u32) a; return; }
+	u64 k = lane < L ? ((key[off + lane] & 0xFFFFFFFFull) << 32) | lane : ~0ull;
+#pragma unroll
+	for (u32 size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+		for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
+			const u64 o = __shfl_xor_sync(0xffffffffu, k, stride);
+			const bool up = (lane & size) == 0;                     // ascending block
+			const bool lower = (lane & stride) == 0;
+			const bool take_min = up == lower;
+			k = take_min ? (o < k ? o : k) : (o > k ? o : k);
+		}
+	}
+	if (lane < L) sidx[off + lane] = off + (u32) (k & 0xFFFFFFFFull);
+}
+
+// long segments: rank by counting (keys are distinct: the position breaks ties), one block per segment
+__global__ void __launch_bounds__(256) seg_sort_long_kernel(const u64 *__restrict__ key, const u32 *__restrict__ segoff, const u32 *__restrict__ segcnt,
+							     const u32 *__restrict__ long_list, const u32 *__restrict__ n_long, u32 *__restrict__ sidx)
+{
+	__shared__ u32 s_low[2048];
+	for (u32 s = blockIdx.x; s < *n_long; s += gridDim.x) {
+		const u32 a = long_list[s], L = segcnt[a], off = segoff[a];
+		for (u32 i0 = 0; i0 < L; i0 += 256) {
+			const u32 i = i0 + threadIdx.x;
+			const u32 mine = i < L ? (u32) key[off + i] : 0u;
+			u32 rank = 0;
+			for (u32 c0 = 0; c0 < L; c0 += 2048) {                      // candidates staged through shared memory
+				const u32 cn = L - c0 < 2048 ? L - c0 : 2048;
+				__syncthreads();
+				for (u32 j = threadIdx.x; j < cn; j += 256) s_low[j] = (u32) key[off + c0 + j];
+				__syncthreads();
+				if (i < L)
+					for (u32 j = 0; j < cn; j++) {
+						const u32 v = s_low[j];
+						rank += (v < mine) || (v == mine && c0 + j < i);
+					}
+			}
+			if (i < L) sidx[off + rank] = off + i;
+		}
+		__syncthreads();
+	}
 }
 
 // SortIndexes tie quirk: inside a run of equal merits every position receives the run's first
@@ -297,6 +354,12 @@ static int sort_kv(metro_ctx *ctx, u64 *ka, u64 *kb, u32 *va, u32 *vb, i64 n, in
 	return sort_scatter_passes(ctx, st, ctx->sortws, ka, kb, va, vb, n, plan, rk, rv, nullptr, &ctx->launches);
 }
 
+__global__ void ids_descend_kernel(const u64 *id, i64 n, u64 *flag)
+{
+	TID;
+	if (i + 1 < n && id[i] > id[i + 1]) *flag = 1;
+}
+
 // argsort of the halo IDs of one catalogue: rank[h] = position of h in ascending-ID order
 static int id_ranks(metro_ctx *ctx, const DevCatalogue &c, DevBuf &rank_buf, DevBuf *tmp)
 {
@@ -304,6 +367,13 @@ static int id_ranks(metro_ctx *ctx, const DevCatalogue &c, DevBuf &rank_buf, Dev
 	const i64 H = c.n_halos;
 	RES(rank_buf, H * 4);
 	if (H == 0) return METRO_OK;
+	{	// catalogues normally list their halos by ascending ID already: the rank is the index (saves 8 radix passes)
+		u64 *flag = ctx->counters.as<u64>() + 20, descends = 0;
+		CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, sizeof(u64), st));
+		ids_descend_kernel<<<GRID(H), TPB, 0, st>>>(c.halo_id.as<u64>(), H, flag); LAUNCHED();
+		TRY(read_total(ctx, flag, &descends));
+		if (!descends) { iota_kernel<<<GRID(H), TPB, 0, st>>>(rank_buf.as<u32>(), H); LAUNCHED(); return METRO_OK; }
+	}
 	RES(tmp[0], H * 8); RES(tmp[1], H * 8); RES(tmp[2], H * 4); RES(tmp[3], H * 4);
 	copy_u64_kernel<<<GRID(H), TPB, 0, st>>>(c.halo_id.as<u64>(), tmp[0].as<u64>(), H); LAUNCHED();
 	iota_kernel<<<GRID(H), TPB, 0, st>>>(tmp[2].as<u32>(), H); LAUNCHED();
@@ -332,8 +402,16 @@ static int build_tree(metro_ctx *ctx, const DirList &L, i64 H_main, int T, const
 	u32 *merit = S[0].as<u32>();
 	merit_key_kernel<<<GRID(n), TPB, 0, st>>>(L.main, L.other, L.tot, segoff, segcnt, np_main, np_other, n, merit, S[1].as<u64>(), S[3].as<u32>());
 	LAUNCHED();
-	u64 *rk; u32 *sidx;
-	TRY(sort_kv(ctx, S[1].as<u64>(), S[2].as<u64>(), S[3].as<u32>(), S[4].as<u32>(), n, 32 + hbits, &rk, &sidx));
+	// order inside every segment: descending merit, ties by position (== the stable sort on (halo, ~merit))
+	u32 *sidx = S[4].as<u32>();
+	RES(S[6], (H_main + 1) * 4);
+	u32 *n_long = reinterpret_cast<u32 *>(ctx->counters.as<u64>() + 21);
+	CUDA_TRY(ctx, cudaMemsetAsync(n_long, 0, sizeof(u64), st));
+	seg_sort_warp_kernel<<<(unsigned) div_up<i64>(H_main * 32, 256), 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, H_main, sidx, S[6].as<u32>(), n_long);
+	LAUNCHED();
+	seg_sort_long_kernel<<<METRO_NUM_SMS_B200 * 2, 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, S[6].as<u32>(), n_long, sidx);
+	LAUNCHED();
+	(void) hbits;
 	tie_quirk_kernel<<<GRID(n), TPB, 0, st>>>(sidx, L.main, merit, segoff, n, S[5].as<u32>()); LAUNCHED();
 	emit_raw_kernel<<<GRID(n), TPB, 0, st>>>(S[5].as<u32>(), n, T, L.main, L.other, L.nc, merit, segcnt, out_main.as<u32>(),
 						  out_prog.as<i32>(), out_nc.as<i32>(), out_merit.as<u32>());
@@ -358,7 +436,7 @@ static int merge_records(metro_ctx *ctx, const metro_params *prm, HitLayout hl, 
 	if (R > 0) {
 		rec_key_kernel<<<GRID(R), TPB, 0, st>>>(rec_key, R, hl, rank1, S[4].as<u64>(), S[6].as<u32>()); LAUNCHED();
 		u64 *rk;
-		TRY(sort_kv(ctx, S[4].as<u64>(), S[5].as<u64>(), S[6].as<u32>(), S[7].as<u32>(), R, 32 + hbits, &rk, &order));
+		TRY(sort_kv(ctx, S[4].as<u64>(), S[5].as<u64>(), S[6].as<u32>(), S[7].as<u32>(), R, 2 * hbits, &rk, &order));
 		head_flag_kernel<<<GRID(R), TPB, 0, st>>>(rk, R, S[8].as<u32>()); LAUNCHED();
 		TRY(scan_exclusive_u32(ctx, st, S[8].as<u32>(), S[9].as<u32>(), R, cnt + 5));
 		TRY(read_total(ctx, cnt + 5, &tot));
@@ -430,9 +508,9 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	RES(S[25], KB * 4); RES(S[26], KB * 4); RES(S[27], KB * T * 4); RES(S[28], KB * 4);
 	if (KB > 0) {
 		RES(S[40], KB * 8); RES(S[41], KB * 8); RES(S[42], KB * 4); RES(S[43], KB * 4);
-		bwd_key_kernel<<<GRID(KB), TPB, 0, st>>>(B[0].as<u32>(), B[1].as<u32>(), rank0, KB, S[40].as<u64>(), S[42].as<u32>()); LAUNCHED();
+		bwd_key_kernel<<<GRID(KB), TPB, 0, st>>>(B[0].as<u32>(), B[1].as<u32>(), rank0, hbits, KB, S[40].as<u64>(), S[42].as<u32>()); LAUNCHED();
 		u64 *rk; u32 *perm;
-		TRY(sort_kv(ctx, S[40].as<u64>(), S[41].as<u64>(), S[42].as<u32>(), S[43].as<u32>(), KB, 32 + hbits, &rk, &perm));
+		TRY(sort_kv(ctx, S[40].as<u64>(), S[41].as<u64>(), S[42].as<u32>(), S[43].as<u32>(), KB, 2 * hbits, &rk, &perm));
 		gather_dir_kernel<<<GRID(KB), TPB, 0, st>>>(perm, KB, T, B[1].as<u32>(), B[0].as<u32>(), B[3].as<i32>(), B[4].as<i32>(),
 							     S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>());
 		LAUNCHED();

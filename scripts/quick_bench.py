@@ -16,5 +16,5 @@ for i in range(steps):
     t = eng.timings()
     print(f"step {i}: total {t['total']:.3f} ms path {t['path']} | A {t['pack_hist']:.3f} B {t['sort']:.3f} join {t['join']:.3f} "
           f"(C {t['sort_pass_ms'][2]:.3f} D {t['sort_pass_ms'][3]:.3f}) select {t['select']:.3f} | hits {info['n_hits']} pairs {info['n_pairs']} "
-          f"trees {info['n_trees']} tokens {info['n_tokens']} spilled {info['n_table_hits']} launches {t['total_launches']}", flush=True)
+          f"N {sum(info['n_tuples'])} trees {info['n_trees']} tokens {info['n_tokens']} spilled {info['n_table_hits']} launches {t['total_launches']}", flush=True)
 eng.close()

@@ -89,6 +89,18 @@ def main():
         frag += np.array_split(x, 12) if len(x) >= 240 else [x]
     run_case(eng, "many_partners", catalogue(later, 10**6, rng), catalogue(frag, 2 * 10**6, rng), prm, expect_path=1)
 
+    # 6b. one later halo whose particles come from 3500 earlier halos of 14 particles each (3500 candidates above the
+    #     threshold in one tree: the long-segment merit sort) next to halos with 40 candidates (warp sort spill-over)
+    giant = ids[:49_000]
+    pieces = np.array_split(giant, 3500)
+    mids = split(rng, ids[49_000:200_000], 30)
+    mid_pieces = []
+    for x in mids:
+        mid_pieces += np.array_split(x, 40) if len(x) >= 40 * 12 else [x]
+    rest = split(rng, ids[200_000:], 500)
+    run_case(eng, "fragmented_giant", catalogue([giant] + mids + rest, 10**6, rng),
+             catalogue(pieces + mid_pieces + [x[: int(0.9 * len(x))] for x in rest], 2 * 10**6, rng), prm)
+
     # 7. multi-species, ZOOM flavour
     prm6 = mb.make_params(nptypes=6, max_orphan_steps=3, flavour=mb.FLAVOUR_ZOOM_DUP)
     spec = mb.SynthSpec(seed=11, n_halos=3000, n_tuples=600_000, pid_bits=22, shard=0, n_shards=1)
