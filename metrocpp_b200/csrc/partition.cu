@@ -112,3 +112,50 @@ extern "C" int metro_partition_bench(metro_ctx *ctx, const uint64_t *keys_in, ui
 	if (counts_out) CUDA_TRY(ctx, cudaMemcpy(counts_out, g, 257 * 8, cudaMemcpyDeviceToHost));
 	return METRO_OK;
 }
+
+// EXPERIMENT: random 32-byte sector gather bandwidth (decides whether a global-memory hash probe can
+// compete with the second partition shuffle).  Every thread reads `per_thread` pseudo-random sectors of
+// a table of n_sectors x 32 B with `ilp` independent loads in flight and folds them into one word.
+template <int ILP>
+__global__ void __launch_bounds__(256) gather_bench_kernel(const ulonglong4 *__restrict__ table, u64 n_sectors, int per_thread, u64 *__restrict__ out)
+{
+	const u64 t = (u64) blockIdx.x * 256 + threadIdx.x;
+	u64 acc = 0, x = t * 0x9E3779B97F4A7C15ull + 12345;
+	for (int i = 0; i < per_thread; i += ILP) {
+		ulonglong4 v[ILP];
+#pragma unroll
+		for (int q = 0; q < ILP; q++) {
+			x = x * 6364136223846793005ull + 1442695040888963407ull;
+			const u64 idx = __umul64hi(x, n_sectors);                   // uniform in [0, n_sectors)
+			// one 32-byte sector per probe (256-bit load, sm_100)
+			asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[q].x), "=l"(v[q].y), "=l"(v[q].z), "=l"(v[q].w) : "l"(table + idx));
+		}
+#pragma unroll
+		for (int q = 0; q < ILP; q++) acc += v[q].x ^ v[q].y ^ v[q].z ^ v[q].w;
+	}
+	out[t] = acc;
+}
+
+extern "C" int metro_gather_bench(metro_ctx *ctx, const void *table, uint64_t n_sectors, int64_t n_threads, int per_thread, int ilp, uint64_t *out_dev,
+				  float *ms_out)
+{
+	if (!ctx) return METRO_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	const unsigned blocks = (unsigned) (n_threads / 256);
+	float best = 1e30f;
+	for (int r = 0; r < 3; r++) {
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
+		if (ilp == 8) gather_bench_kernel<8><<<blocks, 256, 0, st>>>((const ulonglong4 *) table, n_sectors, per_thread, out_dev);
+		else if (ilp == 4) gather_bench_kernel<4><<<blocks, 256, 0, st>>>((const ulonglong4 *) table, n_sectors, per_thread, out_dev);
+		else gather_bench_kernel<1><<<blocks, 256, 0, st>>>((const ulonglong4 *) table, n_sectors, per_thread, out_dev);
+		CUDA_TRY(ctx, cudaGetLastError());
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));
+		CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		float ms;
+		cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
+		if (ms < best) best = ms;
+	}
+	*ms_out = best;
+	return METRO_OK;
+}

@@ -23,8 +23,15 @@
 
 #include "context.cuh"
 
+#ifndef PT_THREADS
 #define PT_THREADS 256
+#endif
+#ifndef PT_ITEMS
 #define PT_ITEMS 16
+#endif
+#ifndef PT_MINB
+#define PT_MINB 3
+#endif
 #define PT_TILE (PT_THREADS * PT_ITEMS)
 // Fill counters that many blocks bump with global atomics live one per 128-byte line: the L2 atomic
 // unit serialises operations on the same line, not only on the same word.
@@ -42,7 +49,7 @@ __device__ __forceinline__ u64 mix_pid(u64 x, const PartPlan &P)
 }
 
 template <int NB, bool PACK>
-__global__ void __launch_bounds__(PT_THREADS, 3) part_kernel(const u64 *__restrict__ in, const u32 *__restrict__ in_halo, const u8 *__restrict__ in_type,
+__global__ void __launch_bounds__(PT_THREADS, PT_MINB) part_kernel(const u64 *__restrict__ in, const u32 *__restrict__ in_halo, const u8 *__restrict__ in_type,
 							     u64 n, u32 snap, u64 pid_base, KeyLayout L, PartPlan P, u64 *__restrict__ out,
 							     u32 *gcount_in /* level 2: counts of the level-1 regions */,
 							     u32 *gcount_out, u32 *overflow,
@@ -615,7 +622,7 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	const i64 nmax = std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
 	while ((nmax >> tb) > 4000 && tb < 20) tb++;                    // final buckets of 2-4 k keys per catalogue
 	PartPlan P;
-	P.b1 = tb > 18 ? tb - 9 : (tb + 1) / 2;
+	P.b1 = getenv("METRO_B1") ? atoi(getenv("METRO_B1")) : (tb > 18 ? tb - 9 : (tb + 1) / 2);
 	P.b2 = tb - P.b1;
 	if (P.b1 < 8) P.b1 = 8;
 	if (P.b2 < 8) P.b2 = 8;
