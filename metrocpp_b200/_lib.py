@@ -45,7 +45,7 @@ class ResultArrays(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("total", C.c_float), ("pack_hist", C.c_float), ("sort", C.c_float), ("join", C.c_float),
                 ("select", C.c_float), ("exchange", C.c_float), ("sort_launches", C.c_int32), ("total_launches", C.c_int32),
-                ("sort_pass_ms", C.c_float * 8), ("path", C.c_int32)]
+                ("sort_pass_ms", C.c_float * 8), ("path", C.c_int32), ("resident", C.c_int32)]
 
 
 class SynthSpec(C.Structure):

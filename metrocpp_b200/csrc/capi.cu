@@ -224,6 +224,7 @@ static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, cons
 		if (cat->type) CUDA_TRY(ctx, cudaMemcpyAsync(c.type.p, cat->type, (size_t) N, cudaMemcpyHostToDevice, st));
 	}
 	c.n_tuples = N;
+	c.gen = ctx->next_gen++;
 	if ((rc = catalogue_scan_tuples(ctx, c, prm->nptypes))) return rc;
 	c.valid = true;
 	ctx->nptypes = prm->nptypes;
@@ -263,6 +264,7 @@ int metro_catalogue_adopt_device(metro_ctx *ctx, int slot, const metro_params *p
 	c.b_pid = cat->pid; c.b_halo = cat->halo; c.b_type = cat->type;
 	c.n_tuples = cat->n_tuples;
 	if (c.n_tuples == 0) { c.b_pid = nullptr; c.b_halo = nullptr; c.b_type = nullptr; }
+	c.gen = ctx->next_gen++;
 	if ((rc = catalogue_scan_tuples(ctx, c, prm->nptypes))) return rc;
 	c.valid = true;
 	ctx->nptypes = prm->nptypes;
@@ -289,8 +291,14 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	if (c0.n_tuples > 0) pid_base = std::min(pid_base, c0.min_pid);
 	if (c1.n_tuples > 0) pid_base = std::min(pid_base, c1.min_pid);
 	if (pid_base == ~0ull) pid_base = 0;
-	ctx->pid_base = pid_base;
 	int pid_bits = std::max(1, ceil_log2_u64(std::max(c0.max_pid, c1.max_pid) - pid_base));
+	{	// prefer a base that does not move from pair to pair of a chain (0, else a multiple of 2^pid_bits) when it costs no key bit
+		const u64 maxp = std::max(c0.max_pid, c1.max_pid);
+		const u64 aligned = pid_bits < 64 ? (pid_base >> pid_bits) << pid_bits : 0;
+		if (std::max(1, ceil_log2_u64(maxp)) <= pid_bits) pid_base = 0;
+		else if (std::max(1, ceil_log2_u64(maxp - aligned)) <= pid_bits) pid_base = aligned;
+	}
+	ctx->pid_base = pid_base;
 	int halo_bits = std::max(1, ceil_log2_u64(Hmax > 0 ? (u64) (Hmax - 1) : 0));
 	int type_bits = prm->nptypes > 1 ? ceil_log2_u64((u64) prm->nptypes - 1) : 0;
 	if (pid_bits + 1 + halo_bits + type_bits > 64 || 2 * halo_bits + 2 * type_bits > 63) {
@@ -313,16 +321,45 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	//  * LSD radix sort by pid + run-length join (any size; also the fallback when a bucket overflows)
 	i64 R = 0, hits = 0;
 	int sort_launches = 0;
-	PartPlan PP;
 	static const bool force_lsd = getenv("METRO_FORCE_LSD") && atoi(getenv("METRO_FORCE_LSD"));
-	bool part = !force_lsd && partition_join_plan(ctx, L, N, &PP);
+	static const bool no_resident = getenv("METRO_NO_RESIDENT") && atoi(getenv("METRO_NO_RESIDENT"));
 	ctx->timings.path = 0;
-	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-	if (part) {
-		bool fell_back = false;
-		if ((rc = stage_partition_join(ctx, L, PP, &R, &hits, &fell_back))) return rc;
-		if (fell_back) part = false;
-		else { ctx->timings.path = 1; sort_launches = 4; }
+	ctx->timings.resident = 0;
+	bool part = false;
+	KeyLayout Lp = L;                                       // layout the partition path runs with
+	if (!force_lsd) {
+		// chain step: the buckets of catalogue 0 are resident if its tuples are the ones they were built from and
+		// this pair fits the layout and plan they were built with
+		PartResident &Rs = ctx->resident;
+		const i64 nmax = std::max(c0.n_tuples, c1.n_tuples);
+		bool reuse0 = !no_resident && Rs.cat0 && Rs.gen == c0.gen && c0.n_tuples > 0 && Rs.L.type_bits == type_bits && halo_bits <= Rs.L.halo_bits &&
+			      pid_base >= Rs.pid_base && nmax <= Rs.nmax_cap &&
+			      ceil_log2_u64(std::max(c0.max_pid, c1.max_pid) - Rs.pid_base) <= Rs.L.pid_bits;
+		static const bool dbg = getenv("METRO_DEBUG") != nullptr;
+		if (dbg && Rs.cat0 && !reuse0)
+			fprintf(stderr, "[metro] resident buckets not reused: gen %d type %d halo %d (%d<=%d) base %d (%llu>=%llu) nmax %d (%lld<=%lld) pidbits %d\n",
+				Rs.gen == c0.gen, Rs.L.type_bits == type_bits, halo_bits <= Rs.L.halo_bits, halo_bits, Rs.L.halo_bits, pid_base >= Rs.pid_base,
+				(unsigned long long) pid_base, (unsigned long long) Rs.pid_base, nmax <= Rs.nmax_cap, (long long) nmax, (long long) Rs.nmax_cap,
+				ceil_log2_u64(std::max(c0.max_pid, c1.max_pid) - Rs.pid_base) <= Rs.L.pid_bits);
+		for (int attempt = reuse0 ? 0 : 1; attempt < 2 && !part; attempt++) {
+			PartPlan PP;
+			bool fell_back = false;
+			if (attempt == 0) {
+				PP = Rs.P; Lp = Rs.L; ctx->pid_base = Rs.pid_base;
+			} else {
+				// a fresh plan; one spare halo bit so that the token halos of the next shifts still fit the layout
+				const int hb = (halo_bits + 1 + 2 * type_bits <= 31 && pid_bits + 2 + halo_bits + type_bits <= 64) ? halo_bits + 1 : halo_bits;
+				Lp = make_key_layout(pid_bits, hb, type_bits);
+				ctx->pid_base = pid_base;
+				i64 ncap = 0;
+				if (!partition_join_plan(ctx, Lp, N, &PP, &ncap)) break;
+				Rs.nmax_cap = ncap;
+			}
+			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+			if ((rc = stage_partition_join(ctx, Lp, PP, halo_bits, attempt == 0, &R, &hits, &fell_back))) return rc;
+			if (!fell_back) { part = true; ctx->timings.path = 1; ctx->timings.resident = attempt == 0; sort_launches = 4; }
+		}
+		if (!part) ctx->pid_base = pid_base;
 	}
 	if (!part) {
 		if ((rc = dev_reserve(ctx, ctx->keys_a, (size_t) N * 8 + 16))) return rc;

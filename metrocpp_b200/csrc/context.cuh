@@ -34,6 +34,7 @@ struct DevCatalogue {
 	const u32 *b_halo = nullptr;
 	const u8 *b_type = nullptr;
 	u64 max_pid = 0, min_pid = 0;
+	u64 gen = 0;            // changes whenever the tuples of this slot change (metro_ctx::next_gen)
 	bool valid = false;
 	const u64 *d_pid() const { return b_pid ? b_pid : pid.as<u64>(); }
 	const u32 *d_halo() const { return b_pid ? b_halo : halo.as<u32>(); }
@@ -46,6 +47,32 @@ struct DevResult {
 	metro_result_info info;
 	DevBuf raw_off[2], raw_prog[2], raw_ncommon[2], raw_merit[2];
 	DevBuf tree_main, tree_orphan, tree_off, clean_prog, clean_ncommon, token_halo;
+};
+
+struct PartPlan {
+	int b1, b2;                 // bucket bits of the two levels
+	int r1;                     // level-1 regions are split in r1 replicas (block index mod r1): r1 x fewer atomics per counter
+	int shift1, shift2;         // key >> shift & (2^b - 1)
+	u64 cap1, cap2;             // capacity of a level-1 (catalogue, bucket, replica) region / a final bucket (keys)
+	u32 tiles1;                 // tiles per level-1 region (= ceil(cap1 / PT_TILE))
+	int pid_bits;
+	u64 mul1, mul2;
+	int xs;
+};
+
+// Final key buckets that stay in HBM between the pairs of a chain: after metro_match_pair the
+// buckets of catalogue 1 are kept; metro_shift makes them the buckets of the new catalogue 0 (its token
+// tuples, appended behind the old catalogue-1 tuples, are still missing: tail0); the next pair then
+// partitions only the new catalogue 1 and that tail, provided its keys fit the same layout and plan.
+struct PartResident {
+	bool cat1 = false, cat0 = false;
+	u64 gen = 0;                // DevCatalogue::gen of the catalogue the buckets belong to
+	int half0 = 0, half1 = 1;   // which half of keys_b (and of the level-2 fill counters) holds catalogue 0 / 1
+	PartPlan P;
+	KeyLayout L;
+	u64 pid_base = 0;
+	i64 nmax_cap = 0;           // tuples per catalogue the plan was sized for
+	i64 tail0 = 0;
 };
 
 struct metro_ctx {
@@ -62,6 +89,8 @@ struct metro_ctx {
 	DevBuf table;                   // pair-count hash table (overflow of the per-halo cache)
 	DevBuf pair_cache;              // 4 (tag,count) ways per catalogue-0 halo
 	DevBuf part_counts;             // partition path: bucket fill counters + overflow flag
+	PartResident resident;
+	u64 next_gen = 1;
 	DevBuf scratch[80];             // select pipeline temporaries
 	DevBuf scan_tmp;                // block sums of the scan primitive
 	DevBuf counters;                // small device counters (u64[64])
@@ -87,19 +116,9 @@ int scan_exclusive_u32(metro_ctx *ctx, cudaStream_t st, const u32 *in, u32 *out,
 
 // ---- pipeline stages -----------------------------------------------------------------------------
 int stage_pack_hist(metro_ctx *ctx, const KeyLayout &L, const SortPlan &plan);      // join.cu
-struct PartPlan {
-	int b1, b2;                 // bucket bits of the two levels
-	int r1;                     // level-1 regions are split in r1 replicas (block index mod r1): r1 x fewer atomics per counter
-	int shift1, shift2;         // key >> shift & (2^b - 1)
-	u64 cap1, cap2;             // capacity of a level-1 (bucket, replica) region / a final bucket (keys)
-	u32 tiles1;                 // tiles per level-1 region (= ceil(cap1 / PT_TILE))
-	int pid_bits;
-	u64 mul1, mul2;
-	int xs;
-};
 
-bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out);                       // join.cu
-int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, i64 *n_records, i64 *n_hits, bool *fell_back);
+bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap);     // partjoin.cu
+int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back);
 int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 n,
 		     i64 *n_records, i64 *n_hits);                                     // join.cu
 int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &L, const u64 *recA_key, const u32 *recA_cnt, i64 RA,

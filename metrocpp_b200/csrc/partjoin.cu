@@ -201,6 +201,32 @@ struct HitPlan {
 #define HIT_MAX_PARTS 1024
 #define HIT_EMPTY 0xFFFFFFFFu
 
+// catalogue-0 tuples per hit partition when pass A does not read the catalogue (its buckets are resident):
+// 16 bytes per lane and load, warp-uniform fast path like the one inside pass A
+__global__ void __launch_bounds__(256) hit_hist_kernel(const u32 *__restrict__ halo, u64 n, int log_hp, u32 nbh, u32 *__restrict__ t0)
+{
+	__shared__ u32 s_hist[HIT_MAX_PARTS];
+	for (u32 i = threadIdx.x; i < nbh; i += 256) s_hist[i] = 0;
+	__syncthreads();
+	const u32 lane = threadIdx.x & 31;
+	const u64 stride = (u64) gridDim.x * 256 * 4;
+	for (u64 i = ((u64) blockIdx.x * 256 + threadIdx.x) * 4; i < ((n + 127) & ~127ull); i += stride) {      // whole warps stay in the loop
+		u32 d[4];
+#pragma unroll
+		for (int q = 0; q < 4; q++) d[q] = i + q < n ? halo[i + q] >> log_hp : 0xFFFFFFFFu;
+		const u32 d0 = __shfl_sync(0xffffffffu, d[0], 0);
+		const bool same = d[0] == d0 && d[1] == d0 && d[2] == d0 && d[3] == d0;
+		if (__all_sync(0xffffffffu, same)) {
+			if (lane == 0 && d0 < nbh) atomicAdd(&s_hist[d0], 128u);
+		} else {
+#pragma unroll
+			for (int q = 0; q < 4; q++) if (d[q] < nbh) atomicAdd(&s_hist[d[q]], 1u);
+		}
+	}
+	__syncthreads();
+	for (u32 i = threadIdx.x; i < nbh; i += 256) { const u32 c = s_hist[i]; if (c) atomicAdd(&t0[i], c); }
+}
+
 // block-wide exclusive scan of one u64 per thread (1024 threads)
 __device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64 *s_warp /* [32] */, u64 *total)
 {
@@ -254,7 +280,8 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_plan_kernel(const u32 *__re
 // cell hash of the pid bits that vary inside a bucket (the top bits of the mixed pid are the bucket number)
 __device__ __forceinline__ u32 bj_hash(u64 r) { return ((u32) r ^ (u32) (r >> 32)) * 0x9E3779B1u; }
 
-__global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ gcount, u64 n_buckets, u64 cap2,
+__global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *__restrict__ keys0, const u64 *__restrict__ keys1,
+								    const u32 *__restrict__ gcount0, const u32 *__restrict__ gcount1, u64 cap2,
 								    KeyLayout L, u64 rmask, HitPlan hp, const u64 *__restrict__ hit_base,
 								    const u32 *__restrict__ hit_cap, u32 *hit_cnt, u64 *__restrict__ hits_out,
 								    u64 *counters, u32 *overflow)
@@ -274,9 +301,9 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 	__shared__ u32 s_n3, s_nhits, s_warpsum[BJ_THREADS / 32];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const u64 g = blockIdx.x;
-	const u32 n0 = gcount[g], n1 = gcount[n_buckets + g];
+	const u32 n0 = gcount0[g], n1 = gcount1[g];
 	if (n0 == 0 || n1 == 0 || (u64) n0 > cap2 || (u64) n1 > cap2) return;       // nothing to join / overflow flagged by the partition pass already
-	const u64 *src0 = keys + g * cap2, *src1 = keys + (n_buckets + g) * cap2;
+	const u64 *src0 = keys0 + g * cap2, *src1 = keys1 + g * cap2;
 	for (int i = tid; i < BJ_NB1 + BJ_NB2; i += BJ_THREADS) cnt1[i] = 0; // cnt2 follows cnt1
 	if (tid == 0) { s_n3 = 0; s_nhits = 0; }
 	u32 ovf = 0;                // overflow causes: 2 table full, 4 hit staging full, 8 hit region full
@@ -612,7 +639,7 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 static size_t part_smem(int nb) { return (size_t) PT_TILE * 8 + (size_t) nb * 16 + (size_t) HIT_MAX_PARTS * 4; }
 
 // Is the partition path applicable, and with which bucket bits?
-bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out)
+bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap)
 {
 	static const i64 min_n = getenv("METRO_PART_MIN_N") ? atoll(getenv("METRO_PART_MIN_N")) : (1ll << 23);
 	if (N < min_n || L.pid_bits < 16) return false;                 // small pairs: the LSD path is fine
@@ -620,7 +647,7 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	if (ctx->cat[0].n_halos > ((i64) HIT_MAX_PARTS << (11 + HR_MAX_SUB_LOG))) return false;
 	int tb = 0;
 	const i64 nmax = std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
-	while ((nmax >> tb) > 4000 && tb < 20) tb++;                    // final buckets of 2-4 k keys per catalogue
+	while ((nmax >> tb) > 3900 && tb < 20) tb++;                    // final buckets of 2-4 k keys per catalogue
 	PartPlan P;
 	P.b1 = getenv("METRO_B1") ? atoi(getenv("METRO_B1")) : (tb > 18 ? tb - 9 : (tb + 1) / 2);
 	P.b2 = tb - P.b1;
@@ -631,8 +658,11 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	P.shift1 = L.pid_shift + L.pid_bits - P.b1;
 	P.shift2 = P.shift1 - P.b2;
 	P.r1 = 8;
-	// regions and buckets exist once per catalogue and are sized for the larger one
-	const double m1 = (double) nmax / (double) ((1ll << P.b1) * P.r1), m2 = (double) nmax / (double) (1ll << (P.b1 + P.b2));
+	// regions and buckets exist once per catalogue and are sized for the larger one, plus 1/8 so that the next
+	// catalogues of a chain (and the token tuples they accumulate) fit the same plan (resident buckets, see PartResident)
+	const i64 ncap = nmax + nmax / 8;
+	if (nmax_cap) *nmax_cap = ncap;
+	const double m1 = (double) ncap / (double) ((1ll << P.b1) * P.r1), m2 = (double) ncap / (double) (1ll << (P.b1 + P.b2));
 	P.cap1 = (u64) (m1 + 8.0 * sqrt(m1) + 4096.0);
 	P.cap1 = (P.cap1 + 1) & ~1ull;                                  // keep regions 16-byte aligned
 	P.cap2 = (u64) (m2 + 9.0 * sqrt(m2) + 64.0);
@@ -645,10 +675,12 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	return true;
 }
 
-static HitPlan make_hit_plan(const KeyLayout &L, i64 H0)
+// rec_halo_bits: halo field width of the hit records (a function of the halo counts only, so that every rank of a
+// multi-GPU run packs its records alike; the key layout may reserve more halo bits)
+static HitPlan make_hit_plan(int rec_halo_bits, int type_bits, i64 H0)
 {
 	HitPlan hp;
-	hp.rec_a_shift = L.halo_bits + 2 * L.type_bits;
+	hp.rec_a_shift = rec_halo_bits + 2 * type_bits;
 	hp.ways = 4; hp.log_hs = 11;                                    // 2048 halos x 4 ways x 8 B = 64 KB: two pass-D blocks per SM
 	hp.log_hp = 11;
 	auto parts = [&](int lg) { return (u64) div_up<i64>(std::max<i64>(H0, 1), 1ll << lg); };
@@ -699,14 +731,16 @@ static int launch_reduce(metro_ctx *ctx, const HitPlan &hp, const u64 *hits, con
 // count u32[R]; the same pair may appear more than once).  *fell_back = true: an overflow flag was
 // raised (nothing usable was produced; the caller runs the LSD path).  Timing events: ev[1] after
 // pass A, ev[2] after pass B, ev[10] after pass C (pass D ends at the caller's ev[3]).
-int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, i64 *n_records, i64 *n_hits, bool *fell_back)
+// reuse0: the final buckets of catalogue 0 are resident (PartResident): only its tail (token tuples) and catalogue 1
+// go through passes A and B.
+int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back)
 {
 	cudaStream_t st = ctx->stream;
 	*fell_back = false;
 	const DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
 	const u64 nbk = 1ull << (P.b1 + P.b2);                                 // buckets per catalogue
 	const u64 nb1 = 2 * (1ull << P.b1) * P.r1, nb = 2 * nbk;                // level-1 regions, final buckets (both catalogues)
-	const HitPlan hp = make_hit_plan(L, c0.n_halos);
+	const HitPlan hp = make_hit_plan(rec_halo_bits, L.type_bits, c0.n_halos);
 	const u64 hits_cap = 2ull * (u64) c0.n_tuples + (u64) (hp.slack + 2) * hp.nbh;
 	const u64 rec_cap = 16ull * (u64) (c0.n_halos + c1.n_halos) + (1ull << 20);
 	int rc;
@@ -726,14 +760,29 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	u64 *hit_base = reinterpret_cast<u64 *>(ctx->part_counts.as<unsigned char>() + off_base);
 	uint4 *units = reinterpret_cast<uint4 *>(ctx->part_counts.as<unsigned char>() + off_units);
 	u64 *counters = ctx->counters.as<u64>();
-	CUDA_TRY(ctx, cudaMemsetAsync(g1, 0, n32 * 4, st));
+	PartResident &R = ctx->resident;
+	const int half0 = reuse0 ? R.half0 : 0, half1 = 1 - half0;          // halves of keys_b / g2 that hold catalogue 0 / 1
+	R.cat0 = false; R.cat1 = false;                                     // re-established at the end
+	// everything is cleared except (reuse0) the level-2 fill counters of the resident half
+	CUDA_TRY(ctx, cudaMemsetAsync(g1, 0, (size_t) (g2 - g1) * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(g2 + (size_t) half1 * nbk, 0, (size_t) nbk * 4, st));
+	if (!reuse0) CUDA_TRY(ctx, cudaMemsetAsync(g2 + (size_t) half0 * nbk, 0, (size_t) nbk * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(t0, 0, (size_t) (2 * HIT_MAX_PARTS + 16) * 4, st));
 	CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 8 * sizeof(u64), st));
-	// pass A: both catalogues (catalogue 0 first; the order inside a bucket is irrelevant)
+	// pass A: both catalogues (the order inside a bucket is irrelevant); the catalogue number handed to the kernel
+	// only selects the half of the region / bucket arrays
 	for (int s = 0; s < 2; s++) {
 		const DevCatalogue &c = ctx->cat[s];
-		if (c.n_tuples == 0) continue;
-		if ((rc = launch_part<true>(ctx, P.b1, (unsigned) div_up<i64>(c.n_tuples, PT_TILE), c.d_pid(), c.d_halo(), c.d_type(), (u64) c.n_tuples, (u32) s, L, P,
-					    ctx->keys_a.as<u64>(), nullptr, g1, ovf, s == 0 ? t0 : nullptr, hp))) return rc;
+		const i64 first = (s == 0 && reuse0) ? std::min(R.tail0, c.n_tuples) : 0, cnt = c.n_tuples - first;
+		if (s == 0 && reuse0 && c.n_tuples > 0) {
+			// the resident part is not read: count its tuples per hit range from the halo column alone
+			hit_hist_kernel<<<METRO_NUM_SMS_B200 * 8, 256, 0, st>>>(c.d_halo(), (u64) first, hp.log_hp, hp.nbh, t0);
+			CUDA_TRY(ctx, cudaGetLastError());
+			ctx->launches++;
+		}
+		if (cnt <= 0) continue;
+		if ((rc = launch_part<true>(ctx, P.b1, (unsigned) div_up<i64>(cnt, PT_TILE), c.d_pid() + first, c.d_halo() + first, c.d_type() ? c.d_type() + first : nullptr,
+					    (u64) cnt, (u32) (s == 0 ? half0 : half1), L, P, ctx->keys_a.as<u64>(), nullptr, g1, ovf, s == 0 ? t0 : nullptr, hp))) return rc;
 	}
 	// hit regions: exact catalogue-0 tuple count per halo range (counted by pass A) -> capacity and base
 	hit_plan_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(t0, hp.nbh, hp.slack, hit_base, hit_cap);
@@ -750,7 +799,9 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 		if (!attr) { CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BJ_SMEM)); attr = true; }
 		const int rb = L.pid_bits - P.b1 - P.b2;
 		const u64 rmask = rb >= 64 ? ~0ull : ((1ull << rb) - 1ull);
-		bucket_join_kernel<<<(unsigned) nbk, BJ_THREADS, BJ_SMEM, st>>>(ctx->keys_b.as<u64>(), g2, nbk, P.cap2, L, rmask, hp, hit_base, hit_cap, hit_cnt,
+		const u64 *kb = ctx->keys_b.as<u64>();
+		bucket_join_kernel<<<(unsigned) nbk, BJ_THREADS, BJ_SMEM, st>>>(kb + (size_t) half0 * nbk * P.cap2, kb + (size_t) half1 * nbk * P.cap2, g2 + (size_t) half0 * nbk,
+										g2 + (size_t) half1 * nbk, P.cap2, L, rmask, hp, hit_base, hit_cap, hit_cnt,
 										ctx->keys_a.as<u64>(), counters, ovf);
 		CUDA_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
@@ -776,5 +827,7 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	*n_hits = (i64) ctx->h_counters[0];
 	*n_records = (i64) ctx->h_counters[2];
 	ctx->res.info.n_table_hits = (i64) ctx->h_counters[5];
+	// the buckets of catalogue 1 stay: after metro_shift they are the buckets of the next pair's catalogue 0
+	R.cat1 = true; R.gen = c1.gen; R.half0 = half0; R.half1 = half1; R.P = P; R.L = L; R.pid_base = ctx->pid_base;
 	return METRO_OK;
 }

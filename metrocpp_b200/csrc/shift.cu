@@ -169,6 +169,13 @@ int stage_shift(metro_ctx *ctx, const metro_params *prm)
 	n0.max_pid = std::max(c1.max_pid, extra > 0 ? c0.max_pid : (u64) 0);
 	n0.min_pid = c1.n_tuples > 0 ? (extra > 0 ? std::min(c1.min_pid, c0.min_pid) : c1.min_pid) : (extra > 0 ? c0.min_pid : 0);
 	n0.valid = true;
+	n0.gen = ctx->next_gen++;
+	// resident key buckets of the old catalogue 1 now belong to the new catalogue 0; its tuples [0, N1) are the old
+	// catalogue-1 tuples in the same order, the token tuples behind them are not in the buckets yet
+	PartResident &R = ctx->resident;
+	if (R.cat1 && R.gen == c1.gen) { R.cat0 = true; R.gen = n0.gen; R.half0 = R.half1; R.half1 = 1 - R.half0; R.tail0 = N1; }
+	else R.cat0 = false;
+	R.cat1 = false;
 	// release the old catalogues (owned buffers only)
 	DevBuf *old0[] = {&c0.halo_id, &c0.npart, &c0.npart_tot, &c0.n_orphan_steps, &c0.is_token, &c0.pid, &c0.halo, &c0.type};
 	for (DevBuf *b : old0) dev_free(*b);

@@ -236,6 +236,7 @@ extern "C" int metro_synth_pair_device(metro_ctx *ctx, const metro_params *prm, 
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	for (int s = 0; s < 2; s++) {
 		TRY(catalogue_scan_tuples(ctx, *cs[s], T));
+		cs[s]->gen = ctx->next_gen++;
 		cs[s]->valid = true;
 	}
 	ctx->nptypes = T;

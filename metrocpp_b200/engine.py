@@ -190,7 +190,7 @@ class MetroEngine:
     def timings(self) -> dict:
         t = _lib.Timings()
         self._check(self.lib.metro_get_timings(self.h, C.byref(t)))
-        d = {k: getattr(t, k) for k in ("total", "pack_hist", "sort", "join", "select", "exchange", "sort_launches", "total_launches", "path")}
+        d = {k: getattr(t, k) for k in ("total", "pack_hist", "sort", "join", "select", "exchange", "sort_launches", "total_launches", "path", "resident")}
         d["sort_pass_ms"] = list(t.sort_pass_ms)
         return d
 

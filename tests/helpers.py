@@ -44,7 +44,7 @@ def flavour_settings(flavour: str):
     return nptypes, noptype, fl
 
 
-def engine_run_chain(eng: mb.MetroEngine, snapshots: list, params: dict, flavour: str, check_oracle: bool = True) -> dict:
+def engine_run_chain(eng: mb.MetroEngine, snapshots: list, params: dict, flavour: str, check_oracle: bool = True, on_step=None) -> dict:
     """The reference's main loop (src/main.cpp:154-308) through the C ABI:
     upload -> match -> fetch -> WriteTree text -> shift, one step per older snapshot."""
     nptypes, noptype, fl = flavour_settings(flavour)
@@ -60,6 +60,8 @@ def engine_run_chain(eng: mb.MetroEngine, snapshots: list, params: dict, flavour
         ocat1 = binding.catalogue_from_snapshot(s, nptypes, noptype)
         eng.upload(1, prm, from_oracle_catalogue(ocat1, noptype))
         res = eng.find_progenitors_and_clean(prm)
+        if on_step is not None:
+            on_step(eng, res)
         if check_oracle:
             compare_result_with_oracle(res, binding.match_pair(oprm, ocat0, ocat1))
         out[number0] = binding.mtree_text(ocat0, ocat1, res.tree_main, res.tree_orphan, res.tree_off, res.clean_prog,

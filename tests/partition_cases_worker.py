@@ -107,6 +107,22 @@ def main():
     c0, c1 = mb.synth_pair_host(prm6, spec, 0), mb.synth_pair_host(prm6, spec, 1)
     run_case(eng, "multi_species_zoom", c0, c1, prm6, expect_path=1)
 
+    # 7b. a chain on the partition path: from the second pair on, the key buckets of catalogue 0 are the resident buckets
+    #     of the previous pair's catalogue 1 (+ the token tuples appended by the shift); every step is checked against the
+    #     oracle, in both token flavours (ZOOM doubles the token tuples)
+    from tests.cases import make_chain
+    for flavour, seed in (("gather", 21), ("zoom", 22)):
+        chain = make_chain(seed=seed, n_snaps=6, n_halos=1500, mean_size=250, p_vanish=0.03)
+        steps = []
+        engine_run_chain(eng, chain, {"minPartHalo": 30, "minPartCmp": 10, "facOrphanSteps": 15, "maxOrphanSteps": 3}, flavour,
+                         on_step=lambda e, r: steps.append((e.timings()["path"], e.timings()["resident"], r.info["n_tokens"])))
+        assert len(steps) == 5 and all(p == 1 for p, _, _ in steps), steps
+        # resident from the second pair on, unless the catalogue outgrows the plan (the ZOOM flavour doubles the token tuples
+        # at every orphan step: src/MergerTree.cpp:597-603)
+        assert steps[0][1] == 0 and sum(r for _, r, _ in steps[1:]) >= (3 if flavour == "gather" else 1), steps
+        assert sum(t for _, _, t in steps) > 0, steps                                  # token tuples were appended to resident buckets
+        print(f"CASE resident_chain_{flavour} steps={steps} ok", flush=True)
+
     # 8. the golden chains (tokens, shifts, ties, thresholds) with the partition path wherever it applies
     for name in golden_io.names():
         snaps, params, mtree = golden_io.load(name)
