@@ -17,7 +17,9 @@ void metro_set_error(metro_ctx *ctx, const char *fmt, ...)
 int dev_reserve(metro_ctx *ctx, DevBuf &b, size_t bytes)
 {
 	if (bytes <= b.cap && b.p) return METRO_OK;
-	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+	// growing an existing buffer: leave 1/4 head room, so that the sizes of a chain (which wander by a few percent from
+	// pair to pair) do not cost a cudaFree + cudaMalloc per buffer and pair
+	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; bytes += bytes / 4; }
 	if (bytes < 256) bytes = 256;
 	CUDA_TRY(ctx, cudaMalloc(&b.p, bytes));
 	b.cap = bytes;
