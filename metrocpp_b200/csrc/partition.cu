@@ -159,3 +159,50 @@ extern "C" int metro_gather_bench(metro_ctx *ctx, const void *table, uint64_t n_
 	*ms_out = best;
 	return METRO_OK;
 }
+
+// EXPERIMENT: rate of small shared->global bulk copies (cp.async.bulk, the TMA engine), the candidate for writing
+// the runs of a partition tile without going through the LSU.  Every thread issues `per_thread` copies of `bytes`
+// bytes from the block's shared tile to scattered 16-byte aligned destinations.
+__global__ void __launch_bounds__(256) bulk_store_bench_kernel(u64 *__restrict__ out, u64 out_words, int per_thread, int bytes)
+{
+	__shared__ __align__(128) u64 tile[4096];
+	for (int i = threadIdx.x; i < 4096; i += 256) tile[i] = (u64) blockIdx.x * 4096 + i;
+	__syncthreads();
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	const u32 words = (u32) bytes / 8;
+	const u64 t = (u64) blockIdx.x * 256 + threadIdx.x;
+	u64 x = t * 0x9E3779B97F4A7C15ull + 1;
+	const u32 src = (u32) __cvta_generic_to_shared(tile + ((threadIdx.x * words) & 4095 & ~1u));
+	for (int i = 0; i < per_thread; i++) {
+		x = x * 6364136223846793005ull + 1442695040888963407ull;
+		const u64 slot = __umul64hi(x, out_words / words - 1);
+		u64 *dst = out + slot * words;
+		asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"((u32) bytes) : "memory");
+		if ((i & 7) == 7) {
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+			asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+		}
+	}
+	asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+	asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+extern "C" int metro_bulk_store_bench(metro_ctx *ctx, void *out, uint64_t out_bytes, int blocks, int per_thread, int bytes, float *ms_out)
+{
+	if (!ctx || bytes % 16) return METRO_ERR_INVALID;
+	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	cudaStream_t st = ctx->stream;
+	float best = 1e30f;
+	for (int r = 0; r < 3; r++) {
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[8], st));
+		bulk_store_bench_kernel<<<blocks, 256, 0, st>>>((u64 *) out, out_bytes / 8, per_thread, bytes);
+		CUDA_TRY(ctx, cudaGetLastError());
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[9], st));
+		CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		float ms;
+		cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
+		if (ms < best) best = ms;
+	}
+	*ms_out = best;
+	return METRO_OK;
+}
