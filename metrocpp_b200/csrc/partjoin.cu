@@ -150,17 +150,18 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) part_kernel(const u64 *__
 #pragma unroll
 	for (int w = 0; w < PT_THREADS / 32; w++) pre += (w < warp) ? s_warpsum[w] : 0u;
 	u32 run = pre + incl - sum;
+	// region space is reserved with one global atomic per (tile, bucket); their latency (the L2 round trip under
+	// contention) is hidden behind the shared-memory reorder, which only needs the tile-local offsets
+	u32 g[BPT];
 #pragma unroll
 	for (int k = 0; k < BPT; k++) {
 		const int b = tid * BPT + k;
+		g[k] = 0;
 		if (b < NB) {
 			// pass A: region (catalogue, bucket b, replica); pass B: final bucket (catalogue, level-1 bucket, b) - the replicas merge here
 			const u64 gb = PACK ? (((u64) snap << P.b1) + (u64) b) * P.r1 + (blockIdx.x & (P.r1 - 1)) : (region / P.r1) * NB + (u64) b;
-			const u64 cap = PACK ? P.cap1 : P.cap2;
-			u32 g = loc[k] ? atomicAdd(&gcount_out[PACK ? gb * CSTRIDE : gb], loc[k]) : 0u;
-			if ((u64) g + loc[k] > cap) { *overflow = 1; g = 0; }
+			if (loc[k]) g[k] = atomicAdd(&gcount_out[PACK ? gb * CSTRIDE : gb], loc[k]);
 			s_start[b] = run;
-			s_dst[b] = (i64) (gb * cap + g) - (i64) run;
 			run += loc[k];
 		}
 	}
@@ -170,6 +171,17 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) part_kernel(const u64 *__
 		if (rk[i] == 0xFFFFFFFFu) continue;
 		const u32 d = (u32) (key[i] >> shift) & (NB - 1);
 		s_keys[s_start[d] + rk[i]] = key[i];
+	}
+#pragma unroll
+	for (int k = 0; k < BPT; k++) {
+		const int b = tid * BPT + k;
+		if (b < NB) {
+			const u64 gb = PACK ? (((u64) snap << P.b1) + (u64) b) * P.r1 + (blockIdx.x & (P.r1 - 1)) : (region / P.r1) * NB + (u64) b;
+			const u64 cap = PACK ? P.cap1 : P.cap2;
+			u32 g0 = g[k];
+			if ((u64) g0 + loc[k] > cap) { *overflow = 1; g0 = 0; }
+			s_dst[b] = (i64) (gb * cap + g0) - (i64) s_start[b];
+		}
 	}
 	__syncthreads();
 #pragma unroll 4
