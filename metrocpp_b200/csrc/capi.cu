@@ -17,9 +17,12 @@ void metro_set_error(metro_ctx *ctx, const char *fmt, ...)
 int dev_reserve(metro_ctx *ctx, DevBuf &b, size_t bytes)
 {
 	if (bytes <= b.cap && b.p) return METRO_OK;
-	// growing an existing buffer: leave 1/4 head room, so that the sizes of a chain (which wander by a few percent from
-	// pair to pair) do not cost a cudaFree + cudaMalloc per buffer and pair
-	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; bytes += bytes / 4; }
+	// 1/4 head room when an existing buffer grows, and from the start for everything below 1 GB: record and pair counts
+	// wander by a few entries from run to run (which slice sees a pair first) and by a few percent from pair to pair of a
+	// chain; without head room that costs a cudaFree + cudaMalloc (tens of ms, and a stall of every rank of a multi-GPU
+	// run in the next collective) per buffer
+	if (b.p || bytes < (1ull << 30)) bytes += bytes / 4 + 4096;
+	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 	if (bytes < 256) bytes = 256;
 	CUDA_TRY(ctx, cudaMalloc(&b.p, bytes));
 	b.cap = bytes;

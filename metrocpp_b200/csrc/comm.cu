@@ -12,6 +12,9 @@
 //     filter, one of the token flags (4 B per catalogue-0 halo) before the shift.
 #include <nccl.h>
 
+#include <chrono>
+#include <stdlib.h>
+
 #include "context.cuh"
 
 #define NCCL_TRY(ctx, expr)                                                                       \
@@ -127,6 +130,9 @@ int comm_exchange_records(metro_ctx *ctx, int halo_bits, int type_bits, const u6
 	const int W = ctx->world, me = ctx->rank;
 	const i64 chunk0 = range_chunk(ctx->cat[0].n_halos, W), chunk1 = range_chunk(ctx->cat[1].n_halos, W);
 	int rc;
+	static const bool dbg = getenv("METRO_DEBUG") != nullptr;
+	auto now = [&] { cudaStreamSynchronize(st); return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double t0 = dbg ? now() : 0, t1 = 0, t2 = 0, t3 = 0;
 	// counts per destination slot, then the full W x 2W count matrix on every rank
 	if ((rc = dev_reserve(ctx, ctx->xcounts, (size_t) (2 * W) * (W + 2) * sizeof(u64)))) return rc;
 	unsigned long long *d_counts = ctx->xcounts.as<unsigned long long>();                // [2W] mine
@@ -139,10 +145,12 @@ int comm_exchange_records(metro_ctx *ctx, int halo_bits, int type_bits, const u6
 		CUDA_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
 	}
+	if (dbg) t1 = now();
 	NCCL_TRY(ctx, ncclAllGather(d_counts, d_matrix, (size_t) 2 * W, ncclUint64, comm_of(ctx), st));
 	std::vector<u64> matrix((size_t) W * 2 * W);
 	CUDA_TRY(ctx, cudaMemcpyAsync(matrix.data(), d_matrix, matrix.size() * sizeof(u64), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	if (dbg) t2 = now();
 	// send layout: slots in order [A->0 .. A->W-1, B->0 .. B->W-1]
 	std::vector<u64> soff(2 * W + 1, 0);
 	for (int s = 0; s < 2 * W; s++) soff[s + 1] = soff[s] + matrix[(size_t) me * 2 * W + s];
@@ -166,6 +174,7 @@ int comm_exchange_records(metro_ctx *ctx, int halo_bits, int type_bits, const u6
 		CUDA_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
 	}
+	if (dbg) t3 = now();
 	// the all-to-all: 4 messages per peer and direction, all in one NCCL group
 	u64 *sk = ctx->xsend_key.as<u64>(); u32 *sc = ctx->xsend_cnt.as<u32>();
 	u64 *rak = ctx->xrecvA_key.as<u64>(); u32 *rac = ctx->xrecvA_cnt.as<u32>();
@@ -180,6 +189,11 @@ int comm_exchange_records(metro_ctx *ctx, int halo_bits, int type_bits, const u6
 		if (rb) { NCCL_TRY(ctx, ncclRecv(rbk + roffB[p], rb, ncclUint64, p, comm_of(ctx), st)); NCCL_TRY(ctx, ncclRecv(rbc + roffB[p], rb, ncclUint32, p, comm_of(ctx), st)); }
 	}
 	NCCL_TRY(ctx, ncclGroupEnd());
+	if (dbg) {
+		const double t4 = now();
+		fprintf(stderr, "[metro] rank %d exchange: R %lld count %.2f ms, all-gather+sync %.2f ms, reserve+scatter %.2f ms, send/recv %.2f ms (nA %llu nB %llu)\n", me,
+			(long long) R, t1 - t0, t2 - t1, t3 - t2, t4 - t3, (unsigned long long) nA, (unsigned long long) nB);
+	}
 	*recA_key = rak; *recA_cnt = rac; *RA = (i64) nA;
 	*recB_key = rbk; *recB_cnt = rbc; *RB = (i64) nB;
 	ctx->exchange_bytes = (i64) ((soff[2 * W] - matrix[(size_t) me * 2 * W + me] - matrix[(size_t) me * 2 * W + W + me]) * 12);
