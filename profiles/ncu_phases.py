@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Executed instructions and stall samples of one kernel, split at its BAR.SYNC instructions:
-usage ncu_phases.py file.ncu-rep [kernel-index]"""
+usage ncu_phases.py file.ncu-rep [kernel-index | kernel-name-substring]"""
 import csv, subprocess, sys
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
@@ -10,7 +10,8 @@ for r in rows:
         cur = {"name": r[1], "rows": []}; kernels.append(cur)
     elif r and r[0] == "Address": cur["hdr"] = r
     elif cur is not None and len(r) > 5: cur["rows"].append(r)
-k = kernels[int(sys.argv[2]) if len(sys.argv) > 2 else 0]
+sel = sys.argv[2] if len(sys.argv) > 2 else "0"
+k = kernels[int(sel)] if sel.isdigit() else next(x for x in kernels if sel in x["name"])
 h, R = k["hdr"], k["rows"]
 ie, si = h.index("Instructions Executed"), h.index("# Samples")
 tot, stot = sum(int(r[ie]) for r in R), sum(int(r[si]) for r in R)
