@@ -500,14 +500,14 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__r
 	const u64 nsl = c ? (c + slice_max - 1) / slice_max : 0;
 	// longest units first (blocks are scheduled in index order: a heavy unit started last would be the tail):
 	// rank of this partition by its per-unit size, ties by index
-	__shared__ u32 s_size[HIT_MAX_PARTS];
+	__shared__ u32 s_size[HIT_MAX_PARTS], s_nsl[HIT_MAX_PARTS];
 	const u32 usz = nsl ? (u32) ((c + nsl - 1) / nsl) : 0u;
-	s_size[d] = usz;
+	s_size[d] = usz; s_nsl[d] = (u32) nsl;
 	__syncthreads();
 	u32 before_units = 0;
 	for (u32 e = 0; e < nbh; e++) {
 		const u32 z = s_size[e];
-		if (z > usz || (z == usz && e < d)) before_units += z ? (u32) ((hit_cnt[e * CSTRIDE] + (u64) slice_max - 1) / slice_max) : 0u;
+		if (z > usz || (z == usz && e < d)) before_units += s_nsl[e];
 	}
 	u64 tot_units;
 	block_excl_scan_u64(nsl, s_warp, &tot_units);

@@ -155,39 +155,61 @@ __global__ void merit_key_kernel(const u32 *m_main, const u32 *m_other, const i3
 
 // Segmented merit sort: the candidates of one halo (a few, rarely hundreds) are ordered by (descending
 // merit, position) without touching the other segments.  Same order as the stable radix sort on
-// (halo, ~merit) it replaces, at a fraction of the passes.  One warp per segment: up to 32 candidates
-// are sorted in registers by a bitonic network; longer segments are queued for seg_sort_long_kernel.
-__global__ void __launch_bounds__(256) seg_sort_warp_kernel(const u64 *__restrict__ key, const u32 *__restrict__ segoff, const u32 *__restrict__ segcnt,
-							     i64 H, u32 *__restrict__ sidx, u32 *long_list, u32 *n_long)
+// (halo, ~merit) it replaces, at a fraction of the passes.  Three tiers: up to 8 candidates are sorted by
+// 8 lanes in registers (bitonic network, four segments per warp), 9-32 by a whole warp, longer ones by
+// a block (seg_sort_long_kernel); the two upper tiers work from lists filled by the first kernel.
+template <int W>
+__device__ __forceinline__ u64 bitonic_lanes(u64 k, u32 lane)
 {
-	const i64 a = ((i64) blockIdx.x * 256 + threadIdx.x) >> 5;
-	const u32 lane = threadIdx.x & 31;
-	if (a >= H) return;
-	const u32 L = segcnt[a], off = segoff[a];
-	if (L == 0) return;
-	if (L == 1) { if (lane == 0) sidx[off] = off; return; }
-	if (L > 32) { if (lane == 0) long_list[atomicAdd(n_long, 1u)] = (u32) a; return; }
-	u64 k = lane < L ? ((key[off + lane] & 0xFFFFFFFFull) << 32) | lane : ~0ull;
 #pragma unroll
-	for (u32 size = 2; size <= 32; size <<= 1) {
+	for (u32 size = 2; size <= W; size <<= 1) {
 #pragma unroll
 		for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
-			const u64 o = __shfl_xor_sync(0xffffffffu, k, stride);
-			const bool up = (lane & size) == 0;                     // ascending block
+			const u64 o = __shfl_xor_sync(0xffffffffu, k, stride, W);
+			const bool up = (lane & size) == 0 || size == W;        // ascending block (the last merge is ascending)
 			const bool lower = (lane & stride) == 0;
-			const bool take_min = up == lower;
-			k = take_min ? (o < k ? o : k) : (o > k ? o : k);
+			k = (up == lower) ? (o < k ? o : k) : (o > k ? o : k);
 		}
 	}
-	if (lane < L) sidx[off + lane] = off + (u32) (k & 0xFFFFFFFFull);
+	return k;
+}
+
+__global__ void __launch_bounds__(256) seg_sort_small_kernel(const u64 *__restrict__ key, const u32 *__restrict__ segoff, const u32 *__restrict__ segcnt,
+							      i64 H, u32 *__restrict__ sidx, u32 *mid_list, u32 *long_list, u32 *n_lists /* [0] mid, [1] long */)
+{
+	const i64 a = ((i64) blockIdx.x * 256 + threadIdx.x) >> 3;
+	const u32 lane = threadIdx.x & 7;
+	u32 L = 0, off = 0;
+	if (a < H) { L = segcnt[a]; off = segoff[a]; }
+	if (lane == 0) {
+		if (L == 1) sidx[off] = off;
+		else if (L > 32) long_list[atomicAdd(n_lists + 1, 1u)] = (u32) a;
+		else if (L > 8) mid_list[atomicAdd(n_lists, 1u)] = (u32) a;
+	}
+	const bool mine = L >= 2 && L <= 8;
+	u64 k = (mine && lane < L) ? ((key[off + lane] & 0xFFFFFFFFull) << 32) | lane : ~0ull;
+	k = bitonic_lanes<8>(k, lane);                                           // every lane of the warp takes part in the shuffles
+	if (mine && lane < L) sidx[off + lane] = off + (u32) (k & 0xFFFFFFFFull);
+}
+
+__global__ void __launch_bounds__(256) seg_sort_mid_kernel(const u64 *__restrict__ key, const u32 *__restrict__ segoff, const u32 *__restrict__ segcnt,
+							    const u32 *__restrict__ mid_list, const u32 *__restrict__ n_lists, u32 *__restrict__ sidx)
+{
+	const u32 lane = threadIdx.x & 31, n = n_lists[0];
+	for (u32 s = (blockIdx.x * 256 + threadIdx.x) >> 5; s < n; s += gridDim.x * 8) {       // warp-uniform
+		const u32 a = mid_list[s], L = segcnt[a], off = segoff[a];
+		u64 k = lane < L ? ((key[off + lane] & 0xFFFFFFFFull) << 32) | lane : ~0ull;
+		k = bitonic_lanes<32>(k, lane);
+		if (lane < L) sidx[off + lane] = off + (u32) (k & 0xFFFFFFFFull);
+	}
 }
 
 // long segments: rank by counting (keys are distinct: the position breaks ties), one block per segment
 __global__ void __launch_bounds__(256) seg_sort_long_kernel(const u64 *__restrict__ key, const u32 *__restrict__ segoff, const u32 *__restrict__ segcnt,
-							     const u32 *__restrict__ long_list, const u32 *__restrict__ n_long, u32 *__restrict__ sidx)
+							     const u32 *__restrict__ long_list, const u32 *__restrict__ n_lists, u32 *__restrict__ sidx)
 {
 	__shared__ u32 s_low[2048];
-	for (u32 s = blockIdx.x; s < *n_long; s += gridDim.x) {
+	for (u32 s = blockIdx.x; s < n_lists[1]; s += gridDim.x) {
 		const u32 a = long_list[s], L = segcnt[a], off = segoff[a];
 		for (u32 i0 = 0; i0 < L; i0 += 256) {
 			const u32 i = i0 + threadIdx.x;
@@ -404,12 +426,14 @@ static int build_tree(metro_ctx *ctx, const DirList &L, i64 H_main, int T, const
 	LAUNCHED();
 	// order inside every segment: descending merit, ties by position (== the stable sort on (halo, ~merit))
 	u32 *sidx = S[4].as<u32>();
-	RES(S[6], (H_main + 1) * 4);
-	u32 *n_long = reinterpret_cast<u32 *>(ctx->counters.as<u64>() + 21);
-	CUDA_TRY(ctx, cudaMemsetAsync(n_long, 0, sizeof(u64), st));
-	seg_sort_warp_kernel<<<(unsigned) div_up<i64>(H_main * 32, 256), 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, H_main, sidx, S[6].as<u32>(), n_long);
+	RES(S[6], (H_main + 1) * 4); RES(S[7], (H_main + 1) * 4);
+	u32 *n_lists = reinterpret_cast<u32 *>(ctx->counters.as<u64>() + 21);
+	CUDA_TRY(ctx, cudaMemsetAsync(n_lists, 0, sizeof(u64), st));
+	seg_sort_small_kernel<<<(unsigned) div_up<i64>(H_main * 8, 256), 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, H_main, sidx, S[6].as<u32>(), S[7].as<u32>(), n_lists);
 	LAUNCHED();
-	seg_sort_long_kernel<<<METRO_NUM_SMS_B200 * 2, 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, S[6].as<u32>(), n_long, sidx);
+	seg_sort_mid_kernel<<<METRO_NUM_SMS_B200 * 4, 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, S[6].as<u32>(), n_lists, sidx);
+	LAUNCHED();
+	seg_sort_long_kernel<<<METRO_NUM_SMS_B200 * 2, 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, S[7].as<u32>(), n_lists, sidx);
 	LAUNCHED();
 	(void) hbits;
 	tie_quirk_kernel<<<GRID(n), TPB, 0, st>>>(sidx, L.main, merit, segoff, n, S[5].as<u32>()); LAUNCHED();
