@@ -107,7 +107,7 @@ typedef struct {
 	int32_t sort_launches, total_launches;
 	float sort_pass_ms[8];          /* LSD path: per onesweep pass; partition path: [0] = pass A (pack + partition), [1] = pass B (partition),
 	                                 * [2] = pass C (bucket join, hits out), [3] = pass D (hit count) */
-	int32_t path;                   /* 0 = LSD radix sort + run-length join, 1 = partition join */
+	int32_t path;                   /* 0 = LSD radix sort + run-length join, 1 = partition join, 2 = wide-key sort (IDs too wide for the packed key) */
 	int32_t resident;               /* partition join: 1 = the key buckets of catalogue 0 were still resident from the previous pair
 	                                 * of the chain (only catalogue 1 and the token tuples were partitioned) */
 } metro_timings;

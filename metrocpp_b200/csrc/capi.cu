@@ -306,12 +306,13 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	ctx->pid_base = pid_base;
 	int halo_bits = std::max(1, ceil_log2_u64(Hmax > 0 ? (u64) (Hmax - 1) : 0));
 	int type_bits = prm->nptypes > 1 ? ceil_log2_u64((u64) prm->nptypes - 1) : 0;
-	if (pid_bits + 1 + halo_bits + type_bits > 64 || 2 * halo_bits + 2 * type_bits > 63) {
-		metro_set_error(ctx, "key does not fit 64 bits: pid %d + snap 1 + halo %d + type %d bits (wide-key path not built yet)",
-				pid_bits, halo_bits, type_bits);
+	if (2 * halo_bits + 2 * type_bits > 63 || halo_bits + type_bits > 31) {
+		metro_set_error(ctx, "pair record does not fit: 2 x (halo %d + type %d bits)", halo_bits, type_bits);
 		return METRO_ERR_UNSUPPORTED;
 	}
-	const KeyLayout L = make_key_layout(pid_bits, halo_bits, type_bits);
+	// pid | snap | halo | type in one 64-bit word if it fits; else the wide-key front end sorts (pid, payload) pairs
+	const bool wide = pid_bits + 1 + halo_bits + type_bits > 64;
+	const KeyLayout L = make_key_layout(wide ? 64 - 1 - halo_bits - type_bits : pid_bits, halo_bits, type_bits);
 	const SortPlan plan = make_sort_plan(L.pid_shift, L.pid_shift + pid_bits);
 	DevResult &res = ctx->res;
 	res.valid = false;
@@ -332,7 +333,7 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	ctx->timings.resident = 0;
 	bool part = false;
 	KeyLayout Lp = L;                                       // layout the partition path runs with
-	if (!force_lsd) {
+	if (!force_lsd && !wide) {
 		// chain step: the buckets of catalogue 0 are resident if its tuples are the ones they were built from and
 		// this pair fits the layout and plan they were built with
 		PartResident &Rs = ctx->resident;
@@ -366,7 +367,11 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 		}
 		if (!part) ctx->pid_base = pid_base;
 	}
-	if (!part) {
+	if (wide) {
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+		if ((rc = stage_wide_join(ctx, L, pid_bits, &R, &hits, &sort_launches))) return rc;
+		ctx->timings.path = 2;
+	} else if (!part) {
 		if ((rc = dev_reserve(ctx, ctx->keys_a, (size_t) N * 8 + 16))) return rc;
 		if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) N * 8 + 16))) return rc;
 		if ((rc = sort_workspace_reserve(ctx, ctx->sortws, N))) return rc;
@@ -418,7 +423,7 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 		cudaEventElapsedTime(&tm.sort_pass_ms[2], ctx->ev[2], ctx->ev[10]);
 		cudaEventElapsedTime(&tm.sort_pass_ms[3], ctx->ev[10], ctx->ev[3]);
 	}
-	else if (N > 0) for (int p = 0; p < plan.n_pass; p++) cudaEventElapsedTime(&tm.sort_pass_ms[p], ctx->ev_pass[p], ctx->ev_pass[p + 1]);
+	else if (tm.path == 0 && N > 0) for (int p = 0; p < plan.n_pass; p++) cudaEventElapsedTime(&tm.sort_pass_ms[p], ctx->ev_pass[p], ctx->ev_pass[p + 1]);
 	tm.sort_launches = sort_launches;
 	tm.total_launches = ctx->launches;
 	res.valid = true;

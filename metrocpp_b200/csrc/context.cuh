@@ -121,6 +121,7 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back);
 int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 n,
 		     i64 *n_records, i64 *n_hits);                                     // join.cu
+int stage_wide_join(metro_ctx *ctx, const KeyLayout &L, int pid_bits, i64 *n_records, i64 *n_hits, int *sort_launches);   // join.cu
 int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &L, const u64 *recA_key, const u32 *recA_cnt, i64 RA,
 		 const u64 *recB_key, const u32 *recB_cnt, i64 RB, i64 a_lo, i64 a_hi);           // select.cu
 // comm.cu (NCCL; no-ops on a single GPU)

@@ -323,3 +323,98 @@ int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 
 		if (!retry) return METRO_OK;
 	}
 }
+
+// ================================================================================================
+// Wide-key path: particle IDs so wide (hashed 64-bit IDs) that pid + snap + halo + type do not fit
+// one 64-bit word.  The tuples are sorted as (key = pid, value = [snap | halo | type]) pairs with the
+// key/value radix sort (8 passes at most, stable, catalogue 0 packed first), then joined by walking
+// the runs of equal pid.  Same records out as the other two front ends; slower, but no input the
+// reference accepts is refused.
+// ================================================================================================
+__global__ void __launch_bounds__(256) pack_wide_kernel(const u64 *__restrict__ pid, const u32 *__restrict__ halo, const u8 *__restrict__ type, u64 n, u32 snap,
+							 u64 pid_base, int type_bits, u32 type_mask, u64 *__restrict__ key, u32 *__restrict__ val)
+{
+	const u64 i = (u64) blockIdx.x * 256 + threadIdx.x;
+	if (i >= n) return;
+	const u32 t = type ? (u32) type[i] : 1u;
+	key[i] = pid[i] - pid_base;
+	val[i] = (snap << 31) | (halo[i] << type_bits) | (t & type_mask);
+}
+
+__global__ void __launch_bounds__(256) join_count_wide_kernel(const u64 *__restrict__ key, const u32 *__restrict__ val, u64 n, KeyLayout L, CacheWay *cache,
+							       int use_cache, PairEntry *tab, int log_cap, u64 *counters)
+{
+	const u64 i = (u64) blockIdx.x * 256 + threadIdx.x;
+	u32 hits = 0, slow = 0;
+	bool overflow = false;
+	if (i < n && (val[i] >> 31) == 0) {
+		const u64 pid = key[i];
+		const int tsh = L.type_bits;
+		const u32 A = (val[i] & 0x7FFFFFFFu) >> tsh, tA = val[i] & L.type_mask;
+		for (u64 t = i + 1; t < n && key[t] == pid; t++) {
+			const u32 v = val[t];
+			if ((v >> 31) == 0) continue;
+			const u32 B = (v & 0x7FFFFFFFu) >> tsh, tB = v & L.type_mask;
+			hits++;
+			if (use_cache && cache_add(cache + (size_t) A * CACHE_WAYS, (B << (2 * tsh)) | (tA << tsh) | tB)) continue;
+			const u64 hk = ((u64) A << (L.halo_bits + 2 * tsh)) | ((u64) B << (2 * tsh)) | ((u64) tA << tsh) | (u64) tB;
+			slow++;
+			if (!pair_add(tab, log_cap, hk)) overflow = true;
+		}
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) { hits += __shfl_xor_sync(0xffffffffu, hits, off); slow += __shfl_xor_sync(0xffffffffu, slow, off); }
+	if ((threadIdx.x & 31) == 0 && hits) atomicAdd((unsigned long long *) &counters[0], (unsigned long long) hits);
+	if ((threadIdx.x & 31) == 0 && slow) atomicAdd((unsigned long long *) &counters[5], (unsigned long long) slow);
+	if (overflow) counters[1] = 1;
+}
+
+// scratch[0] = rec_key (u64[R]), scratch[1] = rec_cnt (u32[R]); L carries halo_bits / type_bits only (pid_bits is unused)
+int stage_wide_join(metro_ctx *ctx, const KeyLayout &L, int pid_bits, i64 *n_records, i64 *n_hits, int *sort_launches)
+{
+	cudaStream_t st = ctx->stream;
+	const i64 N = ctx->cat[0].n_tuples + ctx->cat[1].n_tuples;
+	int rc;
+	if ((rc = dev_reserve(ctx, ctx->keys_a, (size_t) N * 8 + 16))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) N * 8 + 16))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->scratch[2], (size_t) N * 4 + 16))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->scratch[3], (size_t) N * 4 + 16))) return rc;
+	if ((rc = sort_workspace_reserve(ctx, ctx->sortws, N))) return rc;
+	u64 *ka = ctx->keys_a.as<u64>(), *kb = ctx->keys_b.as<u64>();
+	u32 *va = ctx->scratch[2].as<u32>(), *vb = ctx->scratch[3].as<u32>();
+	i64 off = 0;
+	for (int s = 0; s < 2; s++) {
+		const DevCatalogue &c = ctx->cat[s];
+		if (c.n_tuples > 0) {
+			pack_wide_kernel<<<(unsigned) div_up<i64>(c.n_tuples, 256), 256, 0, st>>>(c.d_pid(), c.d_halo(), c.d_type(), (u64) c.n_tuples, (u32) s, ctx->pid_base,
+												 L.type_bits, L.type_mask, ka + off, va + off);
+			CUDA_TRY(ctx, cudaGetLastError());
+			ctx->launches++;
+		}
+		off += c.n_tuples;
+	}
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+	const SortPlan plan = make_sort_plan(0, pid_bits);
+	u64 *sk = ka; u32 *sv = va;
+	if (N > 0) {
+		if ((rc = sort_clear_hist(ctx, st, ctx->sortws))) return rc;
+		if ((rc = sort_histogram(ctx, st, ctx->sortws, ka, N, plan))) return rc;
+		ctx->launches++;
+		if ((rc = sort_scatter_passes(ctx, st, ctx->sortws, ka, kb, va, vb, N, plan, &sk, &sv, nullptr, &ctx->launches))) return rc;
+	}
+	*sort_launches = N > 0 ? plan.n_pass : 0;
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+	PairCountState pc;
+	for (int attempt = 0;; attempt++) {
+		if ((rc = pair_counts_begin(ctx, L, pc, attempt))) return rc;
+		if (N > 0) {
+			join_count_wide_kernel<<<(unsigned) div_up<i64>(N, 256), 256, 0, st>>>(sk, sv, (u64) N, L, ctx->pair_cache.as<CacheWay>(), pc.use_cache,
+											      ctx->table.as<PairEntry>(), pc.log_cap, ctx->counters.as<u64>());
+			CUDA_TRY(ctx, cudaGetLastError());
+			ctx->launches++;
+		}
+		bool retry;
+		if ((rc = pair_counts_finish(ctx, L, pc, attempt, &retry, n_records, n_hits))) return rc;
+		if (!retry) return METRO_OK;
+	}
+}

@@ -61,6 +61,12 @@ def main():
     order = rng.permutation(len(earlier))
     run_case(eng, "plain", catalogue(later, 10**6, rng), catalogue([earlier[i] for i in order], 2 * 10**6, rng), prm, expect_path=1)
 
+    # 1b. hashed 64-bit particle IDs (pid + snap + halo + type do not fit one 64-bit key): the wide-key front end; the
+    #     trees must be those of the same pair with narrow IDs (only the equality of IDs matters)
+    wide = lambda lists: [x * np.uint64(0x9E3779B97F4A7C15) + np.uint64(1 << 63) for x in lists]     # odd multiplier: a bijection on u64
+    with np.errstate(over="ignore"):
+        run_case(eng, "wide_ids", catalogue(wide(later), 10**6, rng), catalogue(wide([earlier[i] for i in order]), 2 * 10**6, rng), prm, expect_path=2)
+
     # 2. one dominant halo (70 % of all tuples): one hit range is far above the mean and gets sliced
     big = [ids[: int(0.7 * n)]] + split(rng, ids[int(0.7 * n):], 300)
     big1 = [x[: int(0.95 * len(x))] for x in big]
