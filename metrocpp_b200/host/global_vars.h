@@ -6,16 +6,32 @@
 #define METRO_HOST_GLOBAL_VARS_H
 #include <cstdint>
 #include <string>
+#include <memory>
+#include <utility>
 #include <vector>
 
 #include "../../include/metro_b200.h"
 #include "Halo.h"
 #include "MergerTree.h"
 
+// std::allocator that leaves trivially constructible elements uninitialised on resize(): the ingest fills every element
+// itself (in parallel), a serial zero-fill of the three tuple columns first would cost as much as the parse
+template <typename T>
+struct UninitAlloc : std::allocator<T> {
+	template <typename U> struct rebind { using other = UninitAlloc<U>; };
+	UninitAlloc() = default;
+	template <typename U> UninitAlloc(const UninitAlloc<U> &) {}
+	template <typename U, typename... Args> void construct(U *p, Args &&...args)
+	{
+		if constexpr (sizeof...(Args) == 0) ::new ((void *) p) U;
+		else ::new ((void *) p) U(std::forward<Args>(args)...);
+	}
+};
+
 struct TupleSoA {                      // one catalogue's "lines of the _particles files"
-	std::vector<uint64_t> pid;
-	std::vector<uint32_t> halo;    // index into locHalos[i]
-	std::vector<uint8_t> type;
+	std::vector<uint64_t, UninitAlloc<uint64_t>> pid;
+	std::vector<uint32_t, UninitAlloc<uint32_t>> halo;    // index into locHalos[i]
+	std::vector<uint8_t, UninitAlloc<uint8_t>> type;
 	std::vector<int64_t> haloOffset;   // [nHalos + 1] when the tuples are grouped by halo in catalogue order (else empty)
 	void clear()
 	{
