@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) part_kernel(const u64 *__
 	if (hist)
 		for (u32 i = tid; i < nbh; i += PT_THREADS) {
 			const u32 c = s_hist[i];
-			if (c) atomicAdd(&t0[i], c);
+			if (c) atomicAdd(&t0[i * CSTRIDE], c);
 		}
 }
 
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) hit_hist_kernel(const u32 *__restrict__ h
 		}
 	}
 	__syncthreads();
-	for (u32 i = threadIdx.x; i < nbh; i += 256) { const u32 c = s_hist[i]; if (c) atomicAdd(&t0[i], c); }
+	for (u32 i = threadIdx.x; i < nbh; i += 256) { const u32 c = s_hist[i]; if (c) atomicAdd(&t0[i * CSTRIDE], c); }
 }
 
 // block-wide exclusive scan of one u64 per thread (1024 threads)
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_plan_kernel(const u32 *__re
 	__shared__ u64 s_warp[32];
 	const u32 d = threadIdx.x;
 	u64 cap = 0;
-	if (d < nbh) cap = (2ull * t0[d] + slack + 1ull) & ~1ull;
+	if (d < nbh) cap = (2ull * t0[d * CSTRIDE] + slack + 1ull) & ~1ull;
 	if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;                    // 32-bit fill counters; more raises the overflow flag
 	const u64 base = block_excl_scan_u64(cap, s_warp, nullptr);
 	if (d < nbh) { hit_base[d] = base; hit_cap[d] = (u32) cap; }
@@ -761,13 +761,13 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) nb * P.cap2 * 8 + 64))) return rc;
 	if ((rc = dev_reserve(ctx, ctx->scratch[0], (size_t) rec_cap * sizeof(u64)))) return rc;
 	if ((rc = dev_reserve(ctx, ctx->scratch[1], (size_t) rec_cap * sizeof(u32)))) return rc;
-	// small state: [g1 nb1*CSTRIDE][hit_cnt 1024*CSTRIDE][g2 nb][t0 1024][hit_cap 1024][ovf, n_units, pad..16] u32, then hit_base u64[1024],
+	// small state: [g1 nb1*CSTRIDE][hit_cnt 1024*CSTRIDE][t0 1024*CSTRIDE][g2 nb][hit_cap 1024][ovf, n_units, pad..16] u32, then hit_base u64[1024],
 	// units uint4[HR_MAX_UNITS]
-	const size_t n32 = (size_t) nb1 * CSTRIDE + (size_t) HIT_MAX_PARTS * CSTRIDE + nb + 2 * HIT_MAX_PARTS + 16;
+	const size_t n32 = (size_t) nb1 * CSTRIDE + 2 * (size_t) HIT_MAX_PARTS * CSTRIDE + nb + HIT_MAX_PARTS + 16;
 	const size_t off_base = (n32 * 4 + 15) & ~(size_t) 15;
 	const size_t off_units = off_base + (size_t) HIT_MAX_PARTS * 8;
 	if ((rc = dev_reserve(ctx, ctx->part_counts, off_units + (size_t) HR_MAX_UNITS * 16))) return rc;
-	u32 *g1 = ctx->part_counts.as<u32>(), *hit_cnt = g1 + nb1 * CSTRIDE, *g2 = hit_cnt + (size_t) HIT_MAX_PARTS * CSTRIDE, *t0 = g2 + nb, *hit_cap = t0 + HIT_MAX_PARTS;
+	u32 *g1 = ctx->part_counts.as<u32>(), *hit_cnt = g1 + nb1 * CSTRIDE, *t0 = hit_cnt + (size_t) HIT_MAX_PARTS * CSTRIDE, *g2 = t0 + (size_t) HIT_MAX_PARTS * CSTRIDE, *hit_cap = g2 + nb;
 	u32 *ovf = hit_cap + HIT_MAX_PARTS, *n_units = ovf + 1;
 	u64 *hit_base = reinterpret_cast<u64 *>(ctx->part_counts.as<unsigned char>() + off_base);
 	uint4 *units = reinterpret_cast<uint4 *>(ctx->part_counts.as<unsigned char>() + off_units);
@@ -779,7 +779,7 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	CUDA_TRY(ctx, cudaMemsetAsync(g1, 0, (size_t) (g2 - g1) * 4, st));
 	CUDA_TRY(ctx, cudaMemsetAsync(g2 + (size_t) half1 * nbk, 0, (size_t) nbk * 4, st));
 	if (!reuse0) CUDA_TRY(ctx, cudaMemsetAsync(g2 + (size_t) half0 * nbk, 0, (size_t) nbk * 4, st));
-	CUDA_TRY(ctx, cudaMemsetAsync(t0, 0, (size_t) (2 * HIT_MAX_PARTS + 16) * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(hit_cap, 0, (size_t) (HIT_MAX_PARTS + 16) * 4, st));
 	CUDA_TRY(ctx, cudaMemsetAsync(counters, 0, 8 * sizeof(u64), st));
 	// pass A: both catalogues (the order inside a bucket is irrelevant); the catalogue number handed to the kernel
 	// only selects the half of the region / bucket arrays
