@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_plan_kernel(const u32 *__re
 #define BJ_NB2 256              // secondary cells x 4 slots
 #define BJ_N3 32                // last-resort list
 #define BJ_SH 6144              // hits staged per bucket; == 4 * BJ_NB1: the dead table is the sorted buffer
+#define BJ_WCAP (BJ_SH / (BJ_THREADS / 32))   // staging slots per warp
 #define BJ_KPT 10               // keys per thread and catalogue: cap2 <= BJ_THREADS * BJ_KPT
 #define BJ_BK 5                 // keys per thread and load batch
 #define BJ_SMEM ((size_t) BJ_NB1 * 32 + (size_t) BJ_SH * 8 + (size_t) HIT_MAX_PARTS * 16)
@@ -310,14 +311,14 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + HIT_MAX_PARTS);        //                  [HIT_MAX_PARTS] counts, then write cursors
 	static_assert((size_t) BJ_NB2 * 32 + BJ_N3 * 8 + (BJ_NB1 + BJ_NB2) * 4 <= (size_t) HIT_MAX_PARTS * 16, "union overflow");
 	static_assert(BJ_SH == BJ_NB1 * 4 && BJ_KPT % BJ_BK == 0, "layout");
-	__shared__ u32 s_n3, s_nhits, s_warpsum[BJ_THREADS / 32];
+	__shared__ u32 s_n3, s_wcount[BJ_THREADS / 32], s_warpsum[BJ_THREADS / 32];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const u64 g = blockIdx.x;
 	const u32 n0 = gcount0[g], n1 = gcount1[g];
 	if (n0 == 0 || n1 == 0 || (u64) n0 > cap2 || (u64) n1 > cap2) return;       // nothing to join / overflow flagged by the partition pass already
 	const u64 *src0 = keys0 + g * cap2, *src1 = keys1 + g * cap2;
 	for (int i = tid; i < BJ_NB1 + BJ_NB2; i += BJ_THREADS) cnt1[i] = 0; // cnt2 follows cnt1
-	if (tid == 0) { s_n3 = 0; s_nhits = 0; }
+	if (tid == 0) s_n3 = 0;
 	u32 ovf = 0;                // overflow causes: 2 table full, 4 hit staging full, 8 hit region full
 	// build: the first loads fly while the counters are being cleared
 #pragma unroll 1
@@ -357,6 +358,8 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 	const u64 lowmask = (1ull << L.snap_shift) - 1ull;                   // (halo, type) of a table entry
 	const u32 tmask = L.type_mask;
 	// (rolled, one body: the next two members of the thread are already in flight; four were no faster)
+	const u32 wbase = (u32) warp * BJ_WCAP;
+	u32 wpos = 0;                                                        // hits staged by this warp so far (same in all its lanes)
 	u64 ka = tid < n0 ? ld_stream_u64(src0 + tid) : 0ull;
 	u64 kb = tid + BJ_THREADS < n0 ? ld_stream_u64(src0 + tid + BJ_THREADS) : 0ull;
 #pragma unroll 1
@@ -387,51 +390,55 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 #undef BJ_CHK
 			const u64 recA = ((u64) key_halo(L, k0) << hp.rec_a_shift) | ((u64) key_type(L, k0) << tb);
 			auto make_rec = [&](u64 e) { const u64 low = e & lowmask; return recA | ((low >> tb) << (2 * tb)) | (low & tmask); };
-			// first hits of the warp: one shared-memory atomic for all of them
-			const u32 ballot = __ballot_sync(0xffffffffu, m > 0);
-			if (ballot) {
-				u32 b = 0;
-				if (lane == 0) b = atomicAdd(&s_nhits, (u32) __popc(ballot));
-				b = __shfl_sync(0xffffffffu, b, 0);
-				if (m > 0) {
-					const u32 pos = b + __popc(ballot & lanemask_lt());
-					if (pos < BJ_SH) stage[pos] = make_rec(e0);
-				}
-			}
-			if (m > 1) {
-				u32 q = atomicAdd(&s_nhits, m - 1);
-				if (q < BJ_SH) stage[q] = make_rec(e1);
-				if (m > 2) {                                         // three or more memberships: rescan for the rest (rare)
-					u32 seen = 0;
-					auto rest = [&](const u64 *cell, u32 cnt) {
-						for (u32 k = 0; k < cnt; k++) {
-							const u64 e = cell[k];
-							if (((e ^ k0) & pmask) == 0) {
-								if (seen >= 2) { q++; if (q < BJ_SH) stage[q] = make_rec(e); }
-								seen++;
+			// hits go to the warp's own slice of the staging array: positions come from ballots, no shared counter
+			const u32 b1 = __ballot_sync(0xffffffffu, m > 0);
+			if (m > 0) { const u32 pos = wpos + __popc(b1 & lanemask_lt()); if (pos < BJ_WCAP) stage[wbase + pos] = make_rec(e0); }
+			wpos += __popc(b1);
+			const u32 b2 = __ballot_sync(0xffffffffu, m > 1);
+			if (b2) {
+				if (m > 1) { const u32 pos = wpos + __popc(b2 & lanemask_lt()); if (pos < BJ_WCAP) stage[wbase + pos] = make_rec(e1); }
+				wpos += __popc(b2);
+				u32 b3 = __ballot_sync(0xffffffffu, m > 2);
+				while (b3) {                                             // three or more memberships: one lane at a time rescans (rare)
+					const u32 src_lane = __ffs(b3) - 1;
+					b3 &= b3 - 1;
+					u32 extra = 0;
+					if (lane == src_lane) {
+						u32 seen = 0;
+						auto rest = [&](const u64 *cell, u32 cnt) {
+							for (u32 k = 0; k < cnt; k++) {
+								const u64 e = cell[k];
+								if (((e ^ k0) & pmask) == 0) {
+									if (seen >= 2) { if (wpos + extra < BJ_WCAP) stage[wbase + wpos + extra] = make_rec(e); extra++; }
+									seen++;
+								}
 							}
+						};
+						const u32 c1 = __umulhi(hh, BJ_NB1), c2 = (hh >> 8) & (BJ_NB2 - 1);
+						const u32 kc = cnt1[c1], k2 = cnt2[c2];
+						rest(t1 + c1 * 4, kc < 4 ? kc : 4);
+						if (kc > 4) {
+							rest(t2 + c2 * 4, k2 < 4 ? k2 : 4);
+							if (k2 > 4) rest(t3, n3);
 						}
-					};
-					const u32 c1 = __umulhi(hh, BJ_NB1), c2 = (hh >> 8) & (BJ_NB2 - 1);
-					const u32 kc = cnt1[c1], k2 = cnt2[c2];
-					rest(t1 + c1 * 4, kc < 4 ? kc : 4);
-					if (kc > 4) {
-						rest(t2 + c2 * 4, k2 < 4 ? k2 : 4);
-						if (k2 > 4) rest(t3, n3);
 					}
+					wpos += __shfl_sync(0xffffffffu, extra, src_lane);
 				}
 			}
 		}
 	}
+	if (lane == 0) s_wcount[warp] = wpos;
+	if (wpos > BJ_WCAP) { ovf |= 4u; wpos = BJ_WCAP; }
 	__syncthreads();                                                     // table and counters are dead from here on
-	u32 nh = s_nhits;
-	if (nh > BJ_SH) { ovf |= 4u; nh = BJ_SH; }
+	u32 nh = 0;
+#pragma unroll
+	for (int w = 0; w < BJ_THREADS / 32; w++) nh += s_wcount[w] < BJ_WCAP ? s_wcount[w] : BJ_WCAP;
 	if (tid == 0 && nh) atomicAdd((unsigned long long *) &counters[0], (unsigned long long) nh);
 	for (u32 i = tid; i < hp.nbh; i += BJ_THREADS) s_cnt[i] = 0;
 	__syncthreads();
-	// hits per partition
+	// hits per partition (every warp walks its own slice)
 	const int psh = hp.rec_a_shift + hp.log_hp;
-	for (u32 j = tid; j < nh; j += BJ_THREADS) atomicAdd(&s_cnt[(u32) (stage[j] >> psh)], 1u);
+	for (u32 j = lane; j < wpos; j += 32) atomicAdd(&s_cnt[(u32) (stage[wbase + j] >> psh)], 1u);
 	__syncthreads();
 	// exclusive scan of the partition counts (2 per thread), region space reserved with one global atomic each
 	constexpr int BPT = HIT_MAX_PARTS / BJ_THREADS;
@@ -466,8 +473,8 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 		}
 	}
 	__syncthreads();
-	for (u32 j = tid; j < nh; j += BJ_THREADS) {
-		const u64 r = stage[j];
+	for (u32 j = lane; j < wpos; j += 32) {
+		const u64 r = stage[wbase + j];
 		t1[atomicAdd(&s_cnt[(u32) (r >> psh)], 1u)] = r;
 	}
 	__syncthreads();
