@@ -95,3 +95,40 @@ def test_host_program_reproduces_reference_mtree(tmp_path, name):
         for number, text in expect.items():
             got = open(os.path.join(out, f"test_{number:03d}.0.mtree")).read()
             assert got == text, f"{name}/{flavour}/{number}"
+
+
+def _parse_only(cfg, threads):
+    r = subprocess.run([BIN, "--parse-only", cfg], capture_output=True, text=True, env=dict(os.environ, METRO_INGEST_THREADS=str(threads)))
+    assert r.returncode == 0, r.stdout + r.stderr
+    return [dict(f.split("=") for f in ln.split()[1:]) for ln in r.stdout.splitlines() if ln.startswith("PARSED")], r.stderr
+
+
+def test_ingest_grammar_edge_cases(tmp_path):
+    """_particles grammar corners through the chunked parser (reference src/IOSettings.cpp:599-689): several blocks in one
+    file, blank lines between blocks, halos listed in a different order than the _halos file, a halo ID that is not in
+    the catalogue (dropped with a warning), a halo without particles, CRLF-free trailing spaces."""
+    inp = tmp_path / "input"
+    inp.mkdir(); (tmp_path / "output").mkdir()
+    halos = {101: [5, 6, 7], 102: [], 103: [8, 9], 104: [10, 11, 12, 13]}
+    for number, z in ((10, "0.000"), (9, "0.100")):
+        with open(inp / f"snapshot_{number:03d}.z{z}.AHF_halos", "w") as f:
+            f.write("#ID(1) hostHalo(2) numSubStruct(3) Mvir(4) npart(5) Xc Yc Zc VXc VYc VZc\n")
+            for hid, parts in halos.items():
+                f.write(f"{hid} 0 0 1.0e10 {len(parts)} 1 2 3 4 5 6\n")
+        with open(inp / f"snapshot_{number:03d}.z{z}.AHF_particles", "w") as f:
+            # block 1: halos 103 and 101 (out of catalogue order), then a blank line, block 2: 999 (unknown), 104, 102 (empty)
+            f.write("2\n2 103\n8 1\n9 1  \n3 101\n5 1\n6 1\n7 1\n\n3\n2 999\n77 1\n78 1\n4 104\n10 1\n11 1\n12 1\n13 1\n0 102\n")
+    cfg = tmp_path / "config.cfg"
+    cfg.write_text("inputFormat = AHF\nhaloSuffix = AHF_halos\npartSuffix = AHF_particles\nhaloPrefix = snapshot_\npartPrefix = snapshot_\n"
+                   f"cpuString = .\nsplitString = _\npathMetroCpp = {tmp_path}/\npathInput = {inp}/\nboxSize = 1000.0\nnChunks = 1\nnSnapsUse = 2\n"
+                   f"nGrid = 4\npathOutput = {tmp_path}/output/\noutPrefix = t_\noutSuffix = mtree\nminPartHalo = 1\nminPartCmp = 1\nfacOrphanSteps = 15\n"
+                   "cosmologicalModel = Planck\nnTreeChunks = 1\ntreeFlavour = zoom\nnPTypes = 2\nnoPType = 1\n")
+    # expected tuples in file order: (pid, halo index in the _halos order 101,102,103,104 -> 0,1,2,3)
+    exp = [(8, 2), (9, 2), (5, 0), (6, 0), (7, 0), (10, 3), (11, 3), (12, 3), (13, 3)]
+    exp_ck = fnv(p + 0x9E3779B97F4A7C15 * (h + 1) + 1 for p, h in exp)
+    for threads in (1, 2, 5, 16):
+        parsed, err = _parse_only(str(cfg), threads)
+        assert len(parsed) == 2
+        for kv in parsed:
+            assert int(kv["halos"]) == 4 and int(kv["tuples"]) == len(exp) and int(kv["tuple_ck"]) == exp_ck, (threads, kv)
+        assert "2 particle lines belong to halo IDs that are not in the halo catalogue" in err
