@@ -717,8 +717,8 @@ static int launch_part(metro_ctx *ctx, int bits, unsigned grid, const u64 *in, c
 	const size_t smem = part_smem(1 << bits);
 #define PART_CASE(NB)                                                                                                               \
 	case NB: {                                                                                                                  \
-		static bool attr = false;                                                                                           \
-		if (!attr) { CUDA_TRY(ctx, cudaFuncSetAttribute(part_kernel<NB, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr = true; } \
+		/* per device, so not cached in a process-wide static: a few microseconds per launch */                         \
+		CUDA_TRY(ctx, cudaFuncSetAttribute(part_kernel<NB, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));    \
 		part_kernel<NB, PACK><<<grid, PT_THREADS, smem, st>>>(in, ih, it, n, snap, ctx->pid_base, L, P, out, gin, gout, ovf, t0, hp.log_hp, hp.nbh);   \
 		break;                                                                                                              \
 	}
@@ -737,8 +737,7 @@ static int launch_reduce(metro_ctx *ctx, const HitPlan &hp, const u64 *hits, con
 			 u64 *rec_key, u32 *rec_cnt, u64 rec_cap, u32 *ovf)
 {
 	const size_t smem = ((size_t) WAYS << hp.log_hs) * 8 + (size_t) HR_OVF * 12;
-	static size_t attr = 0;
-	if (attr < smem) { CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<WAYS, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); attr = smem; }
+	CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<WAYS, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	hit_reduce_kernel<WAYS, SUB><<<HR_MAX_UNITS << (hp.log_hp - hp.log_hs), HR_THREADS, smem, ctx->stream>>>(hits, hit_base, hit_cnt, units, n_units, hp, rec_key, rec_cnt, rec_cap,
 										   ctx->counters.as<u64>(), ovf);
 	CUDA_TRY(ctx, cudaGetLastError());
@@ -814,8 +813,7 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
 	// pass C
 	{
-		static bool attr = false;
-		if (!attr) { CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BJ_SMEM)); attr = true; }
+		CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BJ_SMEM));
 		const int rb = L.pid_bits - P.b1 - P.b2;
 		const u64 rmask = rb >= 64 ? ~0ull : ((1ull << rb) - 1ull);
 		const u64 *kb = ctx->keys_b.as<u64>();
