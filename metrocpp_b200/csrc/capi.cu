@@ -347,9 +347,13 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 				Rs.gen == c0.gen, Rs.L.type_bits == type_bits, halo_bits <= Rs.L.halo_bits, halo_bits, Rs.L.halo_bits, pid_base >= Rs.pid_base,
 				(unsigned long long) pid_base, (unsigned long long) Rs.pid_base, nmax <= Rs.nmax_cap, (long long) nmax, (long long) Rs.nmax_cap,
 				ceil_log2_u64(std::max(c0.max_pid, c1.max_pid) - Rs.pid_base) <= Rs.L.pid_bits);
-		for (int attempt = reuse0 ? 0 : 1; attempt < 2 && !part; attempt++) {
+		// attempt 0: resident plan; 1: fresh plan; 2, 3: fresh plan with 2x / 4x finer buckets after a per-bucket overflow
+		// (table or hit staging: more memberships per particle than the default bucket size provides for)
+		int finer = ctx->part_finer;
+		for (int attempt = reuse0 ? 0 : 1; attempt < 4 && !part; attempt++) {
 			PartPlan PP;
 			bool fell_back = false;
+			u32 mask = 0;
 			if (attempt == 0) {
 				PP = Rs.P; Lp = Rs.L; ctx->pid_base = Rs.pid_base;
 			} else {
@@ -358,12 +362,16 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 				Lp = make_key_layout(pid_bits, hb, type_bits);
 				ctx->pid_base = pid_base;
 				i64 ncap = 0;
-				if (!partition_join_plan(ctx, Lp, N, &PP, &ncap)) break;
+				if (!partition_join_plan(ctx, Lp, N, &PP, &ncap, finer)) break;
 				Rs.nmax_cap = ncap;
 			}
 			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-			if ((rc = stage_partition_join(ctx, Lp, PP, halo_bits, attempt == 0, &R, &hits, &fell_back))) return rc;
-			if (!fell_back) { part = true; ctx->timings.path = 1; ctx->timings.resident = attempt == 0; sort_launches = 4; }
+			if ((rc = stage_partition_join(ctx, Lp, PP, halo_bits, attempt == 0, &R, &hits, &fell_back, &mask, finer > 0))) return rc;
+			if (!fell_back) { part = true; ctx->timings.path = 1; ctx->timings.resident = attempt == 0; sort_launches = 4; if (attempt >= 1) ctx->part_finer = finer; }
+			else if (attempt >= 1) {
+				if ((mask & ~6u) != 0 || finer >= 2) break;      // region / record overflows are not cured by finer buckets: LSD path
+				finer++;
+			}
 		}
 		if (!part) ctx->pid_base = pid_base;
 	}

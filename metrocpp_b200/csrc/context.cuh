@@ -90,6 +90,7 @@ struct metro_ctx {
 	DevBuf pair_cache;              // 4 (tag,count) ways per catalogue-0 halo
 	DevBuf part_counts;             // partition path: bucket fill counters + overflow flag
 	PartResident resident;
+	int part_finer = 0;             // bucket halvings the last successful partition join needed (tried first next time)
 	u64 next_gen = 1;
 	DevBuf scratch[80];             // select pipeline temporaries
 	DevBuf scan_tmp;                // block sums of the scan primitive
@@ -117,8 +118,9 @@ int scan_exclusive_u32(metro_ctx *ctx, cudaStream_t st, const u32 *in, u32 *out,
 // ---- pipeline stages -----------------------------------------------------------------------------
 int stage_pack_hist(metro_ctx *ctx, const KeyLayout &L, const SortPlan &plan);      // join.cu
 
-bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap);     // partjoin.cu
-int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back);
+bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap, int finer);     // partjoin.cu
+int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back,
+			 u32 *overflow_mask, bool finer_plan);
 int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 n,
 		     i64 *n_records, i64 *n_hits);                                     // join.cu
 int stage_wide_join(metro_ctx *ctx, const KeyLayout &L, int pid_bits, i64 *n_records, i64 *n_hits, int *sort_launches);   // join.cu

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 								    const u32 *__restrict__ gcount0, const u32 *__restrict__ gcount1, u64 cap2,
 								    KeyLayout L, u64 rmask, HitPlan hp, const u64 *__restrict__ hit_base,
 								    const u32 *__restrict__ hit_cap, u32 *hit_cnt, u64 *__restrict__ hits_out,
-								    u64 *counters, u32 *overflow)
+								    u64 *counters, u32 *overflow, u32 wcap /* staging slots per warp, <= BJ_WCAP */)
 {
 	extern __shared__ __align__(16) unsigned char bsm[];
 	u64 *t1 = reinterpret_cast<u64 *>(bsm);                              // [BJ_NB1 * 4] primary cells; later the hits sorted by partition
@@ -392,11 +392,11 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 			auto make_rec = [&](u64 e) { const u64 low = e & lowmask; return recA | ((low >> tb) << (2 * tb)) | (low & tmask); };
 			// hits go to the warp's own slice of the staging array: positions come from ballots, no shared counter
 			const u32 b1 = __ballot_sync(0xffffffffu, m > 0);
-			if (m > 0) { const u32 pos = wpos + __popc(b1 & lanemask_lt()); if (pos < BJ_WCAP) stage[wbase + pos] = make_rec(e0); }
+			if (m > 0) { const u32 pos = wpos + __popc(b1 & lanemask_lt()); if (pos < wcap) stage[wbase + pos] = make_rec(e0); }
 			wpos += __popc(b1);
 			const u32 b2 = __ballot_sync(0xffffffffu, m > 1);
 			if (b2) {
-				if (m > 1) { const u32 pos = wpos + __popc(b2 & lanemask_lt()); if (pos < BJ_WCAP) stage[wbase + pos] = make_rec(e1); }
+				if (m > 1) { const u32 pos = wpos + __popc(b2 & lanemask_lt()); if (pos < wcap) stage[wbase + pos] = make_rec(e1); }
 				wpos += __popc(b2);
 				u32 b3 = __ballot_sync(0xffffffffu, m > 2);
 				while (b3) {                                             // three or more memberships: one lane at a time rescans (rare)
@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 							for (u32 k = 0; k < cnt; k++) {
 								const u64 e = cell[k];
 								if (((e ^ k0) & pmask) == 0) {
-									if (seen >= 2) { if (wpos + extra < BJ_WCAP) stage[wbase + wpos + extra] = make_rec(e); extra++; }
+									if (seen >= 2) { if (wpos + extra < wcap) stage[wbase + wpos + extra] = make_rec(e); extra++; }
 									seen++;
 								}
 							}
@@ -428,11 +428,11 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 		}
 	}
 	if (lane == 0) s_wcount[warp] = wpos;
-	if (wpos > BJ_WCAP) { ovf |= 4u; wpos = BJ_WCAP; }
+	if (wpos > wcap) { ovf |= 4u; wpos = wcap; }
 	__syncthreads();                                                     // table and counters are dead from here on
 	u32 nh = 0;
 #pragma unroll
-	for (int w = 0; w < BJ_THREADS / 32; w++) nh += s_wcount[w] < BJ_WCAP ? s_wcount[w] : BJ_WCAP;
+	for (int w = 0; w < BJ_THREADS / 32; w++) nh += s_wcount[w] < wcap ? s_wcount[w] : wcap;
 	if (tid == 0 && nh) atomicAdd((unsigned long long *) &counters[0], (unsigned long long) nh);
 	for (u32 i = tid; i < hp.nbh; i += BJ_THREADS) s_cnt[i] = 0;
 	__syncthreads();
@@ -658,7 +658,9 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 static size_t part_smem(int nb) { return (size_t) PT_TILE * 8 + (size_t) nb * 16 + (size_t) HIT_MAX_PARTS * 4; }
 
 // Is the partition path applicable, and with which bucket bits?
-bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap)
+// finer: halve the buckets `finer` times (the retry after a bucket's table or hit staging overflowed: catalogues whose
+// particles have many memberships produce more hits per key than the default bucket size provides for)
+bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap, int finer)
 {
 	static const i64 min_n = getenv("METRO_PART_MIN_N") ? atoll(getenv("METRO_PART_MIN_N")) : (1ll << 23);
 	if (N < min_n || L.pid_bits < 16) return false;                 // small pairs: the LSD path is fine
@@ -667,6 +669,7 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	int tb = 0;
 	const i64 nmax = std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
 	while ((nmax >> tb) > 3900 && tb < 20) tb++;                    // final buckets of 2-4 k keys per catalogue
+	tb = std::min(tb + finer, 20);
 	PartPlan P;
 	P.b1 = getenv("METRO_B1") ? atoi(getenv("METRO_B1")) : (tb > 18 ? tb - 9 : (tb + 1) / 2);
 	P.b2 = tb - P.b1;
@@ -751,8 +754,10 @@ static int launch_reduce(metro_ctx *ctx, const HitPlan &hp, const u64 *hits, con
 // pass A, ev[2] after pass B, ev[10] after pass C (pass D ends at the caller's ev[3]).
 // reuse0: the final buckets of catalogue 0 are resident (PartResident): only its tail (token tuples) and catalogue 1
 // go through passes A and B.
-int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back)
+int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back,
+			 u32 *overflow_mask, bool finer_plan)
 {
+	if (overflow_mask) *overflow_mask = 0;
 	cudaStream_t st = ctx->stream;
 	*fell_back = false;
 	const DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
@@ -814,12 +819,15 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	// pass C
 	{
 		CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BJ_SMEM));
+		// test hook: a smaller staging capacity for the default bucket size forces the finer-bucket retry
+		static const u32 test_wcap = getenv("METRO_TEST_WCAP") ? (u32) atoi(getenv("METRO_TEST_WCAP")) : 0u;
+		const u32 wcap = (test_wcap && !finer_plan) ? std::min<u32>(test_wcap, BJ_WCAP) : (u32) BJ_WCAP;
 		const int rb = L.pid_bits - P.b1 - P.b2;
 		const u64 rmask = rb >= 64 ? ~0ull : ((1ull << rb) - 1ull);
 		const u64 *kb = ctx->keys_b.as<u64>();
 		bucket_join_kernel<<<(unsigned) nbk, BJ_THREADS, BJ_SMEM, st>>>(kb + (size_t) half0 * nbk * P.cap2, kb + (size_t) half1 * nbk * P.cap2, g2 + (size_t) half0 * nbk,
 										g2 + (size_t) half1 * nbk, P.cap2, L, rmask, hp, hit_base, hit_cap, hit_cnt,
-										ctx->keys_a.as<u64>(), counters, ovf);
+										ctx->keys_a.as<u64>(), counters, ovf, wcap);
 		CUDA_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
 	}
@@ -836,9 +844,10 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	if (*reinterpret_cast<u32 *>(ctx->h_counters + 60) != 0) {
 		static const bool dbg = getenv("METRO_DEBUG") != nullptr;
-		if (dbg) fprintf(stderr, "[metro] partition join fell back to the LSD path: overflow mask 0x%x (1 key region, 2 bucket table, 4 hit staging, "
-				 "8 hit region, 16 record buffer)\n", *reinterpret_cast<u32 *>(ctx->h_counters + 60));
+		if (dbg) fprintf(stderr, "[metro] partition join attempt overflowed, mask 0x%x (1 key region, 2 bucket table, 4 hit staging, 8 hit region, "
+				 "16 record buffer): retry with finer buckets (2, 4) or LSD path\n", *reinterpret_cast<u32 *>(ctx->h_counters + 60));
 		*fell_back = true;
+		if (overflow_mask) *overflow_mask = *reinterpret_cast<u32 *>(ctx->h_counters + 60);
 		return METRO_OK;
 	}
 	*n_hits = (i64) ctx->h_counters[0];

@@ -39,3 +39,18 @@ def test_full_size_pair_front_ends_agree(halos, tuples, bits):
         #  candidate and drops another inside a run of equal merits, src/utils.cpp:429-449, frequent among small halos)
         assert d["mutual"] and d["merit_sorted"], d
     assert part["n_hits"] > 5e8 and part["n_trees"] > 0.9 * halos
+
+
+@pytest.mark.gpu
+def test_finer_bucket_retry_gives_the_same_trees():
+    """A bucket whose hit staging overflows (catalogues with more memberships per particle than the default bucket size
+    provides for) makes the pair retry with buckets half the size instead of dropping to the LSD path; same trees."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a 180 GB B200")
+    args = (1_000_000, 500_000_000, 30)
+    normal = run({}, args)
+    retried = run({"METRO_TEST_WCAP": "150", "METRO_DEBUG": "1"}, args)
+    assert retried["path"] == 1
+    for k in ("n_hits", "n_pairs", "n_trees", "raw", "clean"):
+        assert normal[k] == retried[k], k

@@ -15,4 +15,4 @@ def test_partition_front_end_cases_vs_oracle():
                        cwd=ROOT, env=env, timeout=900)
     assert r.returncode == 0 and "PARTITION_CASES_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     # the two adversarial inputs took the fallback and said why
-    assert r.stderr.count("fell back to the LSD path") >= 2, r.stderr[-2000:]
+    assert r.stderr.count("partition join attempt overflowed") >= 2, r.stderr[-2000:]
