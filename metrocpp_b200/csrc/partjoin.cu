@@ -36,6 +36,7 @@
 // Fill counters that many blocks bump with global atomics live one per 128-byte line: the L2 atomic
 // unit serialises operations on the same line, not only on the same word.
 #define CSTRIDE 32
+#define HIST_SAMPLE 4
 
 // bijection on pid_bits-bit integers (odd multiplies and xor-shifts are invertible mod 2^bits)
 __device__ __forceinline__ u64 mix_pid(u64 x, const PartPlan &P)
@@ -65,7 +66,9 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) part_kernel(const u64 *__
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int BPT = NB / PT_THREADS > 0 ? NB / PT_THREADS : 1;       // buckets per thread in the scan
 	for (int i = tid; i < NB; i += PT_THREADS) s_cnt[i] = 0;
-	const bool hist = PACK && t0 != nullptr;
+	// the tuples per hit range only size the hit regions (2 hits per tuple + slack): every HIST_SAMPLE-th tile is counted and
+	// scaled, which is exact to within a tile per range; the slack covers that
+	const bool hist = PACK && t0 != nullptr && (blockIdx.x % HIST_SAMPLE) == 0;
 	if (hist) for (u32 i = tid; i < nbh; i += PT_THREADS) s_hist[i] = 0;
 
 	u64 base, count;            // this tile = [base, base + count) of the input stream
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(PT_THREADS, PT_MINB) part_kernel(const u64 *__
 	if (hist)
 		for (u32 i = tid; i < nbh; i += PT_THREADS) {
 			const u32 c = s_hist[i];
-			if (c) atomicAdd(&t0[i * CSTRIDE], c);
+			if (c) atomicAdd(&t0[i * CSTRIDE], c * HIST_SAMPLE);
 		}
 }
 
@@ -708,7 +711,7 @@ static HitPlan make_hit_plan(int rec_halo_bits, int type_bits, i64 H0)
 	auto parts = [&](int lg) { return (u64) div_up<i64>(std::max<i64>(H0, 1), 1ll << lg); };
 	while (parts(hp.log_hp) > HIT_MAX_PARTS && hp.log_hp < 11 + HR_MAX_SUB_LOG) hp.log_hp++;
 	hp.nbh = (u32) parts(hp.log_hp);
-	hp.slack = 2048;
+	hp.slack = 2048 + 2 * HIST_SAMPLE * PT_TILE;                    // + the sampling error of the tuple counts (one tile per range end)
 	return hp;
 }
 
@@ -764,7 +767,7 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	const u64 nbk = 1ull << (P.b1 + P.b2);                                 // buckets per catalogue
 	const u64 nb1 = 2 * (1ull << P.b1) * P.r1, nb = 2 * nbk;                // level-1 regions, final buckets (both catalogues)
 	const HitPlan hp = make_hit_plan(rec_halo_bits, L.type_bits, c0.n_halos);
-	const u64 hits_cap = 2ull * (u64) c0.n_tuples + (u64) (hp.slack + 2) * hp.nbh;
+	const u64 hits_cap = 2ull * ((u64) c0.n_tuples + (u64) HIST_SAMPLE * PT_TILE) + (u64) (hp.slack + 2) * hp.nbh;
 	const u64 rec_cap = 16ull * (u64) (c0.n_halos + c1.n_halos) + (1ull << 20);
 	int rc;
 	// keys_a: level-1 regions, dead after pass B and reused for the hit regions
