@@ -226,16 +226,17 @@ __global__ void __launch_bounds__(256) hit_hist_kernel(const u32 *__restrict__ h
 	const u32 lane = threadIdx.x & 31;
 	const u64 stride = (u64) gridDim.x * 256 * 4;
 	for (u64 i = ((u64) blockIdx.x * 256 + threadIdx.x) * 4; i < ((n + 127) & ~127ull); i += stride) {      // whole warps stay in the loop
+		if (((i >> 12) % HIST_SAMPLE) != 0) continue;                     // every HIST_SAMPLE-th run of 4096 tuples, scaled (like pass A; warp-uniform)
 		u32 d[4];
 #pragma unroll
 		for (int q = 0; q < 4; q++) d[q] = i + q < n ? halo[i + q] >> log_hp : 0xFFFFFFFFu;
 		const u32 d0 = __shfl_sync(0xffffffffu, d[0], 0);
 		const bool same = d[0] == d0 && d[1] == d0 && d[2] == d0 && d[3] == d0;
 		if (__all_sync(0xffffffffu, same)) {
-			if (lane == 0 && d0 < nbh) atomicAdd(&s_hist[d0], 128u);
+			if (lane == 0 && d0 < nbh) atomicAdd(&s_hist[d0], 128u * HIST_SAMPLE);
 		} else {
 #pragma unroll
-			for (int q = 0; q < 4; q++) if (d[q] < nbh) atomicAdd(&s_hist[d[q]], 1u);
+			for (int q = 0; q < 4; q++) if (d[q] < nbh) atomicAdd(&s_hist[d[q]], (u32) HIST_SAMPLE);
 		}
 	}
 	__syncthreads();
