@@ -1,4 +1,7 @@
-// partition.cu -- EXPERIMENT (round 1): non-stable 256-way partition pass with fixed-capacity
+// partition.cu -- MICRO-BENCHMARKS, not part of the C ABI of include/metro_b200.h and not on the product path: the
+// entry points below are called by scripts/*_bench.py only (numbers in profiles/r01_experiments.txt).
+//
+// (1) non-stable 256-way partition pass with fixed-capacity
 // buckets, the building block of an MSD / hash-partition join.  Ranks come from one shared-memory
 // atomic per key (no ballots, no look-back); bucket space is reserved with one global atomic per
 // (tile, bucket).
