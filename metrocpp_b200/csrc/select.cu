@@ -175,9 +175,9 @@ __device__ __forceinline__ u64 bitonic_lanes(u64 k, u32 lane)
 }
 
 __global__ void __launch_bounds__(256) seg_sort_small_kernel(const u64 *__restrict__ key, const u32 *__restrict__ segoff, const u32 *__restrict__ segcnt,
-							      i64 H, u32 *__restrict__ sidx, u32 *mid_list, u32 *long_list, u32 *n_lists /* [0] mid, [1] long */)
+							      i64 lo, i64 H, u32 *__restrict__ sidx, u32 *mid_list, u32 *long_list, u32 *n_lists /* [0] mid, [1] long */)
 {
-	const i64 a = ((i64) blockIdx.x * 256 + threadIdx.x) >> 3;
+	const i64 a = lo + (((i64) blockIdx.x * 256 + threadIdx.x) >> 3);                 // segments [lo, H): the ones this rank owns
 	const u32 lane = threadIdx.x & 7;
 	u32 L = 0, off = 0;
 	if (a < H) { L = segcnt[a]; off = segoff[a]; }
@@ -408,7 +408,7 @@ static int id_ranks(metro_ctx *ctx, const DevCatalogue &c, DevBuf &rank_buf, Dev
 // Per-direction list (grouped by `main`, ascending ID of `other` inside a group) -> raw tree:
 // offsets per main halo, merit sort, tie quirk.  S = 8 scratch buffers.
 struct DirList { const u32 *main, *other; const i32 *nc, *tot; i64 n; };
-static int build_tree(metro_ctx *ctx, const DirList &L, i64 H_main, int T, const i32 *np_main, const i32 *np_other, int hbits,
+static int build_tree(metro_ctx *ctx, const DirList &L, i64 H_main, i64 own_lo, i64 own_hi, int T, const i32 *np_main, const i32 *np_other, int hbits,
 		      DevBuf *S, DevBuf &segcnt_b, DevBuf &segoff_b, DevBuf &out_main, DevBuf &out_prog, DevBuf &out_nc, DevBuf &out_merit)
 {
 	cudaStream_t st = ctx->stream;
@@ -429,7 +429,9 @@ static int build_tree(metro_ctx *ctx, const DirList &L, i64 H_main, int T, const
 	RES(S[6], (H_main + 1) * 4); RES(S[7], (H_main + 1) * 4);
 	u32 *n_lists = reinterpret_cast<u32 *>(ctx->counters.as<u64>() + 21);
 	CUDA_TRY(ctx, cudaMemsetAsync(n_lists, 0, sizeof(u64), st));
-	seg_sort_small_kernel<<<(unsigned) div_up<i64>(H_main * 8, 256), 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, H_main, sidx, S[6].as<u32>(), S[7].as<u32>(), n_lists);
+	// only the halos this rank owns have candidates (multi-GPU: 1/world of them)
+	seg_sort_small_kernel<<<(unsigned) div_up<i64>(std::max<i64>(own_hi - own_lo, 1) * 8, 256), 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, own_lo, own_hi, sidx, S[6].as<u32>(),
+													   S[7].as<u32>(), n_lists);
 	LAUNCHED();
 	seg_sort_mid_kernel<<<METRO_NUM_SMS_B200 * 4, 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, S[6].as<u32>(), n_lists, sidx);
 	LAUNCHED();
@@ -526,7 +528,9 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 
 	// 3. forward raw tree (locMTrees[0])
 	DirList fwd = {S[17].as<u32>(), S[18].as<u32>(), S[19].as<i32>(), S[21].as<i32>(), K};
-	TRY(build_tree(ctx, fwd, H0, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), hbits, S + 40, S[22], S[23], S[24], res.raw_prog[0],
+	i64 b_lo = 0, b_hi = H1;                                  // catalogue-1 halos whose backward trees this rank builds
+	comm_owned_range(ctx, H1, &b_lo, &b_hi);
+	TRY(build_tree(ctx, fwd, H0, a_lo, a_hi, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), hbits, S + 40, S[22], S[23], S[24], res.raw_prog[0],
 		       res.raw_ncommon[0], res.raw_merit[0]));
 	// 4. backward raw tree (locMTrees[1]): same pairs ordered by (B, ID(A)), by-type counts of the 0 side
 	RES(S[25], KB * 4); RES(S[26], KB * 4); RES(S[27], KB * T * 4); RES(S[28], KB * 4);
@@ -540,7 +544,7 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 		LAUNCHED();
 	}
 	DirList bwd = {S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>(), KB};
-	TRY(build_tree(ctx, bwd, H1, T, c1.npart_tot.as<i32>(), c0.npart_tot.as<i32>(), hbits, S + 40, S[29], S[30], S[31], res.raw_prog[1],
+	TRY(build_tree(ctx, bwd, H1, b_lo, b_hi, T, c1.npart_tot.as<i32>(), c0.npart_tot.as<i32>(), hbits, S + 40, S[29], S[30], S[31], res.raw_prog[1],
 		       res.raw_ncommon[1], res.raw_merit[1]));
 	res.info.raw_count[0] = K; res.info.raw_count[1] = KB;
 	for (int d = 0; d < 2; d++) {
@@ -609,7 +613,7 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	}
 	// second SortByMerit (:627-628) with iM = position in the kept list
 	DirList cl = {Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(), Q[6].as<i32>(), C};
-	TRY(build_tree(ctx, cl, H0, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), hbits, S + 40, Q[7], Q[8], Q[9], res.clean_prog,
+	TRY(build_tree(ctx, cl, H0, a_lo, a_hi, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), hbits, S + 40, Q[7], Q[8], Q[9], res.clean_prog,
 		       res.clean_ncommon, Q[10]));
 	RES(res.tree_main, NT * 4); RES(res.tree_orphan, NT); RES(res.tree_off, (NT + 1) * 8); RES(res.token_halo, NK * 4);
 	if (H0 > 0) {
