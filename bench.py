@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument("--pid-bits", type=int, default=0, help="0 = smallest even width that fits")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="tuples per snapshot of the CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="tuples per snapshot of the CPU sample (about 20 s of reference CPU time incl. its file ingest)")
     ap.add_argument("--ref-sample", type=int, default=400_000)
     return ap.parse_args()
 
