@@ -526,8 +526,10 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__r
 	if (d == 0) *n_units = (u32) tot_units;
 }
 
-template <int WAYS, bool SUB>
-__global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__restrict__ hits, const u64 *__restrict__ hit_base,
+// THREADS: 512 with 2048 halos per block (two blocks per SM); 1024 with 4096 halos (one block per SM) in sub-range mode,
+// which halves the number of times a big partition is read
+template <int WAYS, bool SUB, int THREADS>
+__global__ void __launch_bounds__(THREADS) hit_reduce_kernel(const u64 *__restrict__ hits, const u64 *__restrict__ hit_base,
 								 const u32 *__restrict__ hit_cnt, const uint4 *__restrict__ units,
 								 const u32 *__restrict__ n_units, HitPlan hp, u64 *__restrict__ rec_key,
 								 u32 *__restrict__ rec_cnt, u64 rec_cap, u64 *counters, u32 *overflow)
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 	u32 *s_count = s_tag + (size_t) HP * WAYS;                           // [HP * WAYS]
 	u64 *s_okey = reinterpret_cast<u64 *>(s_count + (size_t) HP * WAYS); // [HR_OVF] pairs whose halo ran out of ways: open addressing on the record
 	u32 *s_ocnt = reinterpret_cast<u32 *>(s_okey + HR_OVF);              // [HR_OVF]
-	__shared__ u32 s_warpsum[HR_THREADS / 32];
+	__shared__ u32 s_warpsum[THREADS / 32];
 	__shared__ u64 s_base;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint4 u = units[blockIdx.x >> sub_log];
@@ -550,19 +552,19 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 	u64 per = (cnt + u.z - 1) / u.z;
 	per = (per + 1) & ~1ull;
 	const u64 lo = (u64) u.y * per, hi = lo + per < cnt ? lo + per : cnt;
-	for (u32 i = tid; i < HP * WAYS; i += HR_THREADS) { s_tag[i] = HIT_EMPTY; s_count[i] = 0; }
-	for (u32 i = tid; i < HR_OVF; i += HR_THREADS) { s_okey[i] = ~0ull; s_ocnt[i] = 0; }
+	for (u32 i = tid; i < HP * WAYS; i += THREADS) { s_tag[i] = HIT_EMPTY; s_count[i] = 0; }
+	for (u32 i = tid; i < HR_OVF; i += THREADS) { s_okey[i] = ~0ull; s_ocnt[i] = 0; }
 	__syncthreads();
 	const u64 *src = hits + hit_base[d];
 	const u32 tag_mask = (u32) ((1ull << hp.rec_a_shift) - 1ull);
 	u32 spilled = 0;
 	bool ovf = false;           // record buffer full (cause 16)
 	constexpr int UNR = 8;                      // loads in flight per thread (4: 2.7 ms, 8: 2.4 ms, 16: 2.9 ms)
-	for (u64 j0 = lo + tid; j0 < hi; j0 += (u64) HR_THREADS * UNR) {
+	for (u64 j0 = lo + tid; j0 < hi; j0 += (u64) THREADS * UNR) {
 		u64 r[UNR];
 #pragma unroll
 		for (int q = 0; q < UNR; q++) {
-			const u64 j = j0 + (u64) q * HR_THREADS;
+			const u64 j = j0 + (u64) q * THREADS;
 			r[q] = j < hi ? ld_stream_u64(src + j) : ~0ull;
 		}
 #pragma unroll
@@ -622,8 +624,8 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 	__syncthreads();
 	// emit the live ways + the overflow list
 	u32 live = 0;
-	for (u32 i = tid; i < HP * WAYS; i += HR_THREADS) live += s_tag[i] != HIT_EMPTY;
-	for (u32 i = tid; i < HR_OVF; i += HR_THREADS) live += s_okey[i] != ~0ull;
+	for (u32 i = tid; i < HP * WAYS; i += THREADS) live += s_tag[i] != HIT_EMPTY;
+	for (u32 i = tid; i < HR_OVF; i += THREADS) live += s_okey[i] != ~0ull;
 	u32 incl = live;
 #pragma unroll
 	for (int off = 1; off < 32; off <<= 1) {
@@ -634,13 +636,13 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 	__syncthreads();
 	u32 pre = 0, tot = 0;
 #pragma unroll
-	for (int x = 0; x < HR_THREADS / 32; x++) { const u32 v = s_warpsum[x]; pre += x < warp ? v : 0u; tot += v; }
+	for (int x = 0; x < THREADS / 32; x++) { const u32 v = s_warpsum[x]; pre += x < warp ? v : 0u; tot += v; }
 	if (tid == 0) s_base = tot ? atomicAdd((unsigned long long *) &counters[2], (unsigned long long) tot) : 0ull;
 	__syncthreads();
 	u64 o = s_base + pre + incl - live;
 	if (s_base + tot > rec_cap) ovf = true;
 	else {
-		for (u32 i = tid; i < HP * WAYS; i += HR_THREADS) {
+		for (u32 i = tid; i < HP * WAYS; i += THREADS) {
 			const u32 t = s_tag[i];
 			if (t != HIT_EMPTY) {
 				rec_key[o] = ((u64) ((d << hp.log_hp) + (sub << hp.log_hs) + i / WAYS) << hp.rec_a_shift) | (u64) t;
@@ -648,7 +650,7 @@ __global__ void __launch_bounds__(HR_THREADS) hit_reduce_kernel(const u64 *__res
 				o++;
 			}
 		}
-		for (u32 i = tid; i < HR_OVF; i += HR_THREADS) {
+		for (u32 i = tid; i < HR_OVF; i += THREADS) {
 			const u64 k = s_okey[i];
 			if (k != ~0ull) { rec_key[o] = k; rec_cnt[o] = s_ocnt[i]; o++; }
 		}
@@ -711,6 +713,7 @@ static HitPlan make_hit_plan(int rec_halo_bits, int type_bits, i64 H0)
 	hp.log_hp = 11;
 	auto parts = [&](int lg) { return (u64) div_up<i64>(std::max<i64>(H0, 1), 1ll << lg); };
 	while (parts(hp.log_hp) > HIT_MAX_PARTS && hp.log_hp < 11 + HR_MAX_SUB_LOG) hp.log_hp++;
+	if (hp.log_hp > hp.log_hs) hp.log_hs = 12;                       // sub-range mode: 4096 halos x 4 ways = 128 KB, one 1024-thread block per SM
 	hp.nbh = (u32) parts(hp.log_hp);
 	hp.slack = 2048 + 2 * HIST_SAMPLE * PT_TILE;                    // + the sampling error of the tuple counts (one tile per range end)
 	return hp;
@@ -739,13 +742,13 @@ static int launch_part(metro_ctx *ctx, int bits, unsigned grid, const u64 *in, c
 	return METRO_OK;
 }
 
-template <int WAYS, bool SUB>
+template <int WAYS, bool SUB, int THREADS>
 static int launch_reduce(metro_ctx *ctx, const HitPlan &hp, const u64 *hits, const u64 *hit_base, const u32 *hit_cnt, const uint4 *units, const u32 *n_units,
 			 u64 *rec_key, u32 *rec_cnt, u64 rec_cap, u32 *ovf)
 {
 	const size_t smem = ((size_t) WAYS << hp.log_hs) * 8 + (size_t) HR_OVF * 12;
-	CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<WAYS, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	hit_reduce_kernel<WAYS, SUB><<<HR_MAX_UNITS << (hp.log_hp - hp.log_hs), HR_THREADS, smem, ctx->stream>>>(hits, hit_base, hit_cnt, units, n_units, hp, rec_key, rec_cnt, rec_cap,
+	CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<WAYS, SUB, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	hit_reduce_kernel<WAYS, SUB, THREADS><<<HR_MAX_UNITS << (hp.log_hp - hp.log_hs), THREADS, smem, ctx->stream>>>(hits, hit_base, hit_cnt, units, n_units, hp, rec_key, rec_cnt, rec_cap,
 										   ctx->counters.as<u64>(), ovf);
 	CUDA_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
@@ -840,8 +843,8 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	hit_units_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(hit_cnt, hp.nbh, units, n_units);
 	CUDA_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
-	if (hp.log_hp == hp.log_hs) rc = launch_reduce<4, false>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
-	else rc = launch_reduce<4, true>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
+	if (hp.log_hp == hp.log_hs) rc = launch_reduce<4, false, HR_THREADS>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
+	else rc = launch_reduce<4, true, 2 * HR_THREADS>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
 	if (rc) return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 60, ovf, 4, cudaMemcpyDeviceToHost, st));
