@@ -36,7 +36,7 @@
 // Fill counters that many blocks bump with global atomics live one per 128-byte line: the L2 atomic
 // unit serialises operations on the same line, not only on the same word.
 #define CSTRIDE 32
-#define HIST_SAMPLE 4
+#define HIST_SAMPLE 8
 
 // bijection on pid_bits-bit integers (odd multiplies and xor-shifts are invertible mod 2^bits)
 __device__ __forceinline__ u64 mix_pid(u64 x, const PartPlan &P)
