@@ -106,6 +106,7 @@ void metro_ctx_destroy(metro_ctx *ctx)
 	sort_workspace_free(ctx->sortws);
 	comm_destroy(ctx);
 	dev_free(ctx->keys_a); dev_free(ctx->keys_b); dev_free(ctx->table); dev_free(ctx->pair_cache); dev_free(ctx->scan_tmp); dev_free(ctx->counters);
+	dev_free(ctx->part_counts);
 	for (DevBuf &b : ctx->scratch) dev_free(b);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
@@ -375,6 +376,8 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 		}
 		if (!part) ctx->pid_base = pid_base;
 	}
+	// the wide-key and LSD front ends overwrite keys_a / keys_b: whatever buckets were resident there are gone
+	if (wide || !part) { ctx->resident.cat0 = false; ctx->resident.cat1 = false; }
 	if (wide) {
 		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
 		if ((rc = stage_wide_join(ctx, L, pid_bits, &R, &hits, &sort_launches))) return rc;

@@ -86,15 +86,15 @@ struct __align__(16) PairEntry {
 #define PAIR_EMPTY (~0ull)
 #define PAIR_MAX_PROBE 1024
 
-__device__ __forceinline__ u32 pair_hash(u64 k, int log_cap)
+__device__ __forceinline__ u64 pair_hash(u64 k, int log_cap)
 {
-	return (u32) ((k * 0x9E3779B97F4A7C15ull) >> (64 - log_cap));
+	return (k * 0x9E3779B97F4A7C15ull) >> (64 - log_cap);          // log_cap may exceed 32 (the table grows x4 per retry)
 }
 
 __device__ __forceinline__ bool pair_add(PairEntry *tab, int log_cap, u64 hk)
 {
-	const u32 mask = (1u << log_cap) - 1u;
-	u32 h = pair_hash(hk, log_cap);
+	const u64 mask = (1ull << log_cap) - 1ull;
+	u64 h = pair_hash(hk, log_cap);
 	for (int probe = 0; probe < PAIR_MAX_PROBE; probe++) {
 		PairEntry *e = tab + h;
 		u64 cur = *reinterpret_cast<volatile u64 *>(&e->key);

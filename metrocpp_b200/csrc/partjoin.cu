@@ -15,8 +15,8 @@
 //
 // mix(pid) is a bijection that spreads any ID distribution uniformly, so the key buckets have FIXED
 // capacity (mean + 9 sigma): no digit histograms, no look-back, no stability requirement.  The hit
-// regions are sized from an exact count of the catalogue-0 tuples per halo range (every hit belongs to
-// one catalogue-0 tuple; 2 hits per tuple + slack are provisioned).  Any overflow (adversarial
+// regions are sized from a sampled count of the catalogue-0 tuples per halo range (every hit belongs to
+// one catalogue-0 tuple; 2 hits per tuple + slack for the sampling error are provisioned).  Any overflow (adversarial
 // duplication of one pid, > 2 memberships per particle on average over a whole range) raises a flag and
 // the caller falls back to the LSD sort path of join.cu, which has no such limit.
 #include <stdlib.h>
@@ -263,8 +263,8 @@ __device__ __forceinline__ u64 block_excl_scan_u64(u64 v, u64 *s_warp /* [32] */
 }
 
 // region capacity and base per hit partition (1 block of HIT_MAX_PARTS threads)
-__global__ void __launch_bounds__(HIT_MAX_PARTS) hit_plan_kernel(const u32 *__restrict__ t0, u32 nbh, u32 slack, u64 *__restrict__ hit_base,
-								  u32 *__restrict__ hit_cap)
+__global__ void __launch_bounds__(HIT_MAX_PARTS) hit_plan_kernel(const u32 *__restrict__ t0, u32 nbh, u32 slack, u64 hits_cap, u64 *__restrict__ hit_base,
+								  u32 *__restrict__ hit_cap, u32 *overflow)
 {
 	__shared__ u64 s_warp[32];
 	const u32 d = threadIdx.x;
@@ -272,6 +272,8 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_plan_kernel(const u32 *__re
 	if (d < nbh) cap = (2ull * t0[d * CSTRIDE] + slack + 1ull) & ~1ull;
 	if (cap > 0xFFFFFFF0ull) cap = 0xFFFFFFF0ull;                    // 32-bit fill counters; more raises the overflow flag
 	const u64 base = block_excl_scan_u64(cap, s_warp, nullptr);
+	// never past the allocation (the tuple counts are sampled estimates): a region that does not fit is cut and the flag raised
+	if (d < nbh && base + cap > hits_cap) { cap = base < hits_cap ? (hits_cap - base) & ~1ull : 0; atomicOr(overflow, 8u); }
 	if (d < nbh) { hit_base[d] = base; hit_cap[d] = (u32) cap; }
 }
 
@@ -296,6 +298,74 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_plan_kernel(const u32 *__re
 
 // cell hash of the pid bits that vary inside a bucket (the top bits of the mixed pid are the bucket number)
 __device__ __forceinline__ u32 bj_hash(u64 r) { return ((u32) r ^ (u32) (r >> 32)) * 0x9E3779B1u; }
+
+// Tail of pass C (both table variants): the hits a CTA staged in per-warp slices of `stage` are counted per hit partition,
+// the partitions get their space in the global hit regions (one global atomic each), the hits are sorted by partition into
+// `sorted` (the dead table) and written out in runs.  `ovf` collects overflow causes (4 hit staging full, 8 hit region full).
+__device__ __forceinline__ void bj_flush_hits(const u64 *stage, u64 *sorted, i64 *s_dst, u32 *s_cnt, u32 *s_wcount, u32 *s_warpsum, u32 wbase, u32 wpos, u32 wcap,
+					      const HitPlan &hp, const u64 *__restrict__ hit_base, const u32 *__restrict__ hit_cap, u32 *hit_cnt,
+					      u64 *__restrict__ hits_out, u64 *counters, u32 &ovf)
+{
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	u64 *t1 = sorted;
+	if (lane == 0) s_wcount[warp] = wpos;
+	if (wpos > wcap) { ovf |= 4u; wpos = wcap; }
+	__syncthreads();                                                     // table and counters are dead from here on
+	u32 nh = 0;
+#pragma unroll
+	for (int w = 0; w < BJ_THREADS / 32; w++) nh += s_wcount[w] < wcap ? s_wcount[w] : wcap;
+	if (tid == 0 && nh) atomicAdd((unsigned long long *) &counters[0], (unsigned long long) nh);
+	for (u32 i = tid; i < hp.nbh; i += BJ_THREADS) s_cnt[i] = 0;
+	__syncthreads();
+	// hits per partition (every warp walks its own slice)
+	const int psh = hp.rec_a_shift + hp.log_hp;
+	for (u32 j = lane; j < wpos; j += 32) atomicAdd(&s_cnt[(u32) (stage[wbase + j] >> psh)], 1u);
+	__syncthreads();
+	// exclusive scan of the partition counts (2 per thread), region space reserved with one global atomic each
+	constexpr int BPT = HIT_MAX_PARTS / BJ_THREADS;
+	u32 loc[BPT], sum = 0;
+#pragma unroll
+	for (int k = 0; k < BPT; k++) { const u32 b = tid * BPT + k; loc[k] = b < hp.nbh ? s_cnt[b] : 0u; sum += loc[k]; }
+	u32 incl = sum;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		const u32 v = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane >= off) incl += v;
+	}
+	if (lane == 31) s_warpsum[warp] = incl;
+	__syncthreads();
+	u32 pre = 0;
+#pragma unroll
+	for (int w = 0; w < BJ_THREADS / 32; w++) pre += (w < warp) ? s_warpsum[w] : 0u;
+	u32 run = pre + incl - sum;
+#pragma unroll
+	for (int k = 0; k < BPT; k++) {
+		const u32 b = tid * BPT + k;
+		if (b < hp.nbh) {
+			i64 dst = INT64_MIN;
+			if (loc[k]) {
+				const u32 g0 = atomicAdd(&hit_cnt[b * CSTRIDE], loc[k]);
+				if ((u64) g0 + loc[k] <= (u64) hit_cap[b]) dst = (i64) (hit_base[b] + g0) - (i64) run;
+				else ovf |= 8u;
+			}
+			s_dst[b] = dst;
+			s_cnt[b] = run;                                              // write cursor of the partition inside the sorted buffer
+			run += loc[k];
+		}
+	}
+	__syncthreads();
+	for (u32 j = lane; j < wpos; j += 32) {
+		const u64 r = stage[wbase + j];
+		t1[atomicAdd(&s_cnt[(u32) (r >> psh)], 1u)] = r;
+	}
+	__syncthreads();
+	for (u32 j = tid; j < nh; j += BJ_THREADS) {
+		const u64 r = t1[j];
+		const i64 dst = s_dst[(u32) (r >> psh)];
+		if (dst != INT64_MIN) st_stream_u64(hits_out + dst + (i64) j, r);
+	}
+}
+
 
 __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *__restrict__ keys0, const u64 *__restrict__ keys1,
 								    const u32 *__restrict__ gcount0, const u32 *__restrict__ gcount1, u64 cap2,
@@ -431,62 +501,190 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 			}
 		}
 	}
-	if (lane == 0) s_wcount[warp] = wpos;
-	if (wpos > wcap) { ovf |= 4u; wpos = wcap; }
-	__syncthreads();                                                     // table and counters are dead from here on
-	u32 nh = 0;
-#pragma unroll
-	for (int w = 0; w < BJ_THREADS / 32; w++) nh += s_wcount[w] < wcap ? s_wcount[w] : wcap;
-	if (tid == 0 && nh) atomicAdd((unsigned long long *) &counters[0], (unsigned long long) nh);
-	for (u32 i = tid; i < hp.nbh; i += BJ_THREADS) s_cnt[i] = 0;
-	__syncthreads();
-	// hits per partition (every warp walks its own slice)
-	const int psh = hp.rec_a_shift + hp.log_hp;
-	for (u32 j = lane; j < wpos; j += 32) atomicAdd(&s_cnt[(u32) (stage[wbase + j] >> psh)], 1u);
-	__syncthreads();
-	// exclusive scan of the partition counts (2 per thread), region space reserved with one global atomic each
-	constexpr int BPT = HIT_MAX_PARTS / BJ_THREADS;
-	u32 loc[BPT], sum = 0;
-#pragma unroll
-	for (int k = 0; k < BPT; k++) { const u32 b = tid * BPT + k; loc[k] = b < hp.nbh ? s_cnt[b] : 0u; sum += loc[k]; }
-	u32 incl = sum;
-#pragma unroll
-	for (int off = 1; off < 32; off <<= 1) {
-		const u32 v = __shfl_up_sync(0xffffffffu, incl, off);
-		if (lane >= off) incl += v;
-	}
-	if (lane == 31) s_warpsum[warp] = incl;
-	__syncthreads();
-	u32 pre = 0;
-#pragma unroll
-	for (int w = 0; w < BJ_THREADS / 32; w++) pre += (w < warp) ? s_warpsum[w] : 0u;
-	u32 run = pre + incl - sum;
-#pragma unroll
-	for (int k = 0; k < BPT; k++) {
-		const u32 b = tid * BPT + k;
-		if (b < hp.nbh) {
-			i64 dst = INT64_MIN;
-			if (loc[k]) {
-				const u32 g0 = atomicAdd(&hit_cnt[b * CSTRIDE], loc[k]);
-				if ((u64) g0 + loc[k] <= (u64) hit_cap[b]) dst = (i64) (hit_base[b] + g0) - (i64) run;
-				else ovf |= 8u;
-			}
-			s_dst[b] = dst;
-			s_cnt[b] = run;                                              // write cursor of the partition inside the sorted buffer
-			run += loc[k];
+	bj_flush_hits(stage, t1, s_dst, s_cnt, s_wcount, s_warpsum, wbase, wpos, wcap, hp, hit_base, hit_cap, hit_cnt, hits_out, counters, ovf);
+	if (ovf) atomicOr(overflow, ovf);
+}
+
+// ---- mbarrier + 1-D bulk copy (TMA) helpers -----------------------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 arrivals)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64 *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+{
+	asm volatile("{\n"
+		     ".reg .pred p;\n"
+		     "MBAR_WAIT:\n"
+		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		     "@p bra MBAR_DONE;\n"
+		     "bra MBAR_WAIT;\n"
+		     "MBAR_DONE:\n"
+		     "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion is signalled on `bar`
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, u32 bytes, u64 *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)), "l"(src), "r"(bytes),
+		     "r"(smem_addr(bar)) : "memory");
+}
+
+// ---- pass C, direct-address variant ------------------------------------------------------------
+// mix(pid) is a bijection on pid_bits-bit integers whose top b1+b2 bits are the bucket number, so inside a bucket a particle is
+// identified by the remaining rb = pid_bits - b1 - b2 bits.  Dense IDs (a full box numbers its particles 1..N^3 and about half of
+// them are bound) leave rb <= 14: the catalogue-1 members of the bucket then sit in a DIRECT-ADDRESS table tab[2^rb] of 32-bit
+// payloads ((halo, type) + 1; 0 = empty): no hash, no tag compare, a probe is one 4-byte shared-memory load.  Second and later
+// members of a particle (it is listed under a subhalo and under its host) hang off the slot as a chain of (payload, next) nodes.
+// The catalogue-1 keys of the bucket arrive through 1-D bulk copies (TMA) into the hit staging area, which is idle until the probe:
+// no load instructions, no address arithmetic and no register staging on the build side, and the copies fly while the table is cleared.
+#define BD_NODES 1024           // chain nodes per bucket
+#define BD_FLAG 0x80000000u     // slot / next holds a node index, not a payload
+#define BD_U 4                  // catalogue-0 keys per thread and probe batch
+#define BD_CHUNK 1024           // keys per bulk copy == keys one build sweep of the CTA consumes
+#define BD_MAXCHUNK 6           // BJ_SH / BD_CHUNK
+#define BD_MAX_RB 14             // 64 KB table (one CTA per SM); 13 bits and less: two CTAs per SM
+static size_t bd_front_bytes(int rb) { return std::max(((size_t) 4 << rb) + (size_t) BD_NODES * 8, (size_t) BJ_SH * 8); }
+static size_t bd_smem_bytes(int rb) { return bd_front_bytes(rb) + (size_t) BJ_SH * 8 + (size_t) HIT_MAX_PARTS * 12; }
+
+__global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_direct_kernel(const u64 *__restrict__ keys0, const u64 *__restrict__ keys1,
+									   const u32 *__restrict__ gcount0, const u32 *__restrict__ gcount1, u64 cap2,
+									   KeyLayout L, int rb, u32 front_bytes, HitPlan hp, const u64 *__restrict__ hit_base,
+									   const u32 *__restrict__ hit_cap, u32 *hit_cnt, u64 *__restrict__ hits_out,
+									   u64 *counters, u32 *overflow, u32 wcap /* staging slots per warp, <= BJ_WCAP */)
+{
+	extern __shared__ __align__(128) unsigned char dsm[];
+	u32 *tab = reinterpret_cast<u32 *>(dsm);                             // [2^rb] direct-address slots
+	uint2 *nodes = reinterpret_cast<uint2 *>(tab + (1u << rb));          // [BD_NODES] (payload, next)
+	u64 *sorted = reinterpret_cast<u64 *>(dsm);                          // after the probe: [BJ_SH] hits sorted by partition (table and nodes are dead)
+	u64 *stage = reinterpret_cast<u64 *>(dsm + front_bytes);             // [BJ_SH] build: catalogue-1 keys (TMA destination); probe: hits in discovery order
+	i64 *s_dst = reinterpret_cast<i64 *>(stage + BJ_SH);                 // [HIT_MAX_PARTS]
+	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + HIT_MAX_PARTS);        // [HIT_MAX_PARTS]
+	__shared__ __align__(8) u64 s_bar[BD_MAXCHUNK];
+	__shared__ u32 s_nnodes, s_wcount[BJ_THREADS / 32], s_warpsum[BJ_THREADS / 32];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const u64 g = blockIdx.x;
+	const u32 n0 = gcount0[g], n1 = gcount1[g];
+	if (n0 == 0 || n1 == 0 || (u64) n0 > cap2 || (u64) n1 > cap2) return;       // nothing to join / overflow flagged by the partition pass already
+	const u64 *src0 = keys0 + g * cap2, *src1 = keys1 + g * cap2;
+	const u32 nchunk = (n1 + BD_CHUNK - 1) / BD_CHUNK;
+	if (tid == 0) {
+		s_nnodes = 0;
+		for (u32 c = 0; c < nchunk; c++) mbar_init(&s_bar[c], 1);
+		mbar_init_fence();
+		for (u32 c = 0; c < nchunk; c++) {
+			const u32 have = n1 - c * BD_CHUNK < BD_CHUNK ? n1 - c * BD_CHUNK : BD_CHUNK;
+			const u32 bytes = ((have + 1) & ~1u) * 8;                  // whole 16-byte units (cap2 is even: the pad key is inside the bucket)
+			mbar_expect_tx(&s_bar[c], bytes);
+			tma_load_1d(stage + c * BD_CHUNK, src1 + c * BD_CHUNK, bytes, &s_bar[c]);
 		}
 	}
-	__syncthreads();
-	for (u32 j = lane; j < wpos; j += 32) {
-		const u64 r = stage[wbase + j];
-		t1[atomicAdd(&s_cnt[(u32) (r >> psh)], 1u)] = r;
+	// the first probe batch is requested now and used after the build
+	u64 kn[BD_U];
+#pragma unroll
+	for (int u = 0; u < BD_U; u++) {
+		const u32 j = u * BJ_THREADS + tid;
+		kn[u] = j < n0 ? ld_stream_u64(src0 + j) : 0ull;
 	}
-	__syncthreads();
-	for (u32 j = tid; j < nh; j += BJ_THREADS) {
-		const u64 r = t1[j];
-		const i64 dst = s_dst[(u32) (r >> psh)];
-		if (dst != INT64_MIN) st_stream_u64(hits_out + dst + (i64) j, r);
+	{
+		uint4 *t4 = reinterpret_cast<uint4 *>(tab);
+		for (u32 i = tid; i < (1u << rb) / 4; i += BJ_THREADS) t4[i] = make_uint4(0u, 0u, 0u, 0u);
 	}
+	u32 ovf = 0;                // overflow causes: 2 table (chain nodes) full, 4 hit staging full, 8 hit region full
+	__syncthreads();
+	const u32 rmask = (1u << rb) - 1u;
+	const u32 lowmask = (1u << L.snap_shift) - 1u;                       // (halo, type) of a key
+	const int psft = L.pid_shift;
+	// build
+#pragma unroll 1
+	for (u32 c = 0; c < nchunk; c++) {
+		mbar_wait(&s_bar[c], 0);
+		const u32 j = c * BD_CHUNK + 2 * tid;
+		const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(stage + j);
+		// both compare-and-swaps are issued before either result is looked at
+		u32 r[2], p[2], old[2];
+#pragma unroll
+		for (int q = 0; q < 2; q++) {
+			const u64 k = q ? kk.y : kk.x;
+			r[q] = (u32) (k >> psft) & rmask;
+			p[q] = ((u32) k & lowmask) + 1u;
+		}
+#pragma unroll
+		for (int q = 0; q < 2; q++) old[q] = j + q < n1 ? atomicCAS(&tab[r[q]], 0u, p[q]) : 0u;
+#pragma unroll
+		for (int q = 0; q < 2; q++) {
+			if (old[q] != 0u) {                                          // the particle has a member already: chain this one in front
+				const u32 i = atomicAdd(&s_nnodes, 1u);
+				if (i < BD_NODES) nodes[i] = make_uint2(p[q], atomicExch(&tab[r[q]], BD_FLAG | i));
+				else ovf |= 2u;
+			}
+		}
+	}
+	__syncthreads();                                                     // table complete; the staging area is free for the hits
+	// probe: every member of the slot's chain is one hit
+	const int tb = L.type_bits;
+	const u32 tmask = L.type_mask;
+	const u32 wbase = (u32) warp * BJ_WCAP;
+	u32 wpos = 0;                                                        // hits staged by this warp so far (same in all its lanes)
+	const u32 lt = lanemask_lt();
+#pragma unroll 1
+	for (u32 j0 = 0; j0 < n0; j0 += BD_U * BJ_THREADS) {
+		u64 k[BD_U];
+		u32 v[BD_U];
+#pragma unroll
+		for (int u = 0; u < BD_U; u++) {
+			k[u] = kn[u];
+			const u32 jn = j0 + (BD_U + u) * BJ_THREADS + tid;
+			kn[u] = jn < n0 ? ld_stream_u64(src0 + jn) : 0ull;
+		}
+#pragma unroll
+		for (int u = 0; u < BD_U; u++) {                                 // (a key past the end is 0: slot 0 is read and ignored)
+			const u32 t = tab[(u32) (k[u] >> psft) & rmask];
+			v[u] = j0 + u * BJ_THREADS + tid < n0 ? t : 0u;
+		}
+#pragma unroll
+		for (int u = 0; u < BD_U; u++) {
+			u32 p1 = v[u], p2 = 0, rest = 0;
+			if (p1 & BD_FLAG) { const uint2 nd = nodes[p1 & ~BD_FLAG]; p1 = nd.x; rest = nd.y; }
+			if (rest) {
+				if (rest & BD_FLAG) { const uint2 nd = nodes[rest & ~BD_FLAG]; p2 = nd.x; rest = nd.y; }
+				else { p2 = rest; rest = 0; }
+			}
+			const u32 kl = (u32) k[u];
+			const u64 recA = ((u64) ((u32) (k[u] >> tb) & L.halo_mask) << hp.rec_a_shift) | (u64) ((kl & tmask) << tb);
+			auto make_rec = [&](u32 p) { const u32 pm = p - 1u; return recA | (u64) (((pm >> tb) << (2 * tb)) | (pm & tmask)); };
+			const u32 b1 = __ballot_sync(0xffffffffu, p1 != 0u), b2 = __ballot_sync(0xffffffffu, p2 != 0u);
+			u32 pos = wpos + __popc(b1 & lt) + __popc(b2 & lt);
+			if (p1) { if (pos < wcap) stage[wbase + pos] = make_rec(p1); pos++; }
+			if (p2) { if (pos < wcap) stage[wbase + pos] = make_rec(p2); }
+			wpos += __popc(b1) + __popc(b2);
+			u32 b3 = __ballot_sync(0xffffffffu, rest != 0u);
+			while (b3) {                                                 // three or more memberships: one lane at a time walks the rest of its chain (rare)
+				const u32 src_lane = __ffs(b3) - 1;
+				b3 &= b3 - 1;
+				u32 extra = 0;
+				if (lane == src_lane) {
+					while (rest) {
+						u32 p;
+						if (rest & BD_FLAG) { const uint2 nd = nodes[rest & ~BD_FLAG]; p = nd.x; rest = nd.y; }
+						else { p = rest; rest = 0; }
+						if (wpos + extra < wcap) stage[wbase + wpos + extra] = make_rec(p);
+						extra++;
+					}
+				}
+				wpos += __shfl_sync(0xffffffffu, extra, src_lane);
+			}
+		}
+	}
+	bj_flush_hits(stage, sorted, s_dst, s_cnt, s_wcount, s_warpsum, wbase, wpos, wcap, hp, hit_base, hit_cap, hit_cnt, hits_out, counters, ovf);
 	if (ovf) atomicOr(overflow, ovf);
 }
 
@@ -494,7 +692,7 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_kernel(const u64 *_
 // Work units: a partition, or a slice of a heavy one (a catalogue dominated by one halo); slices of
 // the same partition emit separate records for the same pair, which the selection stage sums.
 #define HR_THREADS 512
-#define HR_OVF 4096             // entries of the per-block hash table for pairs beyond a halo's WAYS slots
+#define HR_OVF 3072             // entries of the per-block hash table for pairs beyond a halo's WAYS slots (36 KB: table + queues + 64 KB of ways = 108 KB, two blocks per SM)
 #define HR_OVF_PROBES 32
 #define HR_MAX_UNITS (2 * HIT_MAX_PARTS)   // sum of ceil(c_d / (3 mean)) <= nbh + nbh / 3
 #define HR_MAX_SUB_LOG 4                   // a partition holds up to 2^4 sub-ranges of 2048 halos: 32 M catalogue-0 halos per GPU
@@ -527,7 +725,12 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__r
 }
 
 // THREADS: 512 with 2048 halos per block (two blocks per SM); 1024 with 4096 halos (one block per SM) in sub-range mode,
-// which halves the number of times a big partition is read
+// which halves the number of times a big partition is read.
+// Fast path per hit: one 16-byte load of the halo's way tags, compare, one shared-memory add.  A hit that finds no way holding its
+// tag (first sight of a pair: a way has to be claimed; or all ways taken: overflow table) is NOT handled in place - 4 % of the hits
+// would drag three quarters of the warp iterations through the slow code with one or two active lanes.  It is pushed on the warp's own
+// small queue (positions from a ballot, no atomics); whenever 32 are queued the warp runs the slow path once with all lanes busy.
+#define HR_QCAP 64              // queue entries per warp: < 32 before a push, <= 32 pushed
 template <int WAYS, bool SUB, int THREADS>
 __global__ void __launch_bounds__(THREADS) hit_reduce_kernel(const u64 *__restrict__ hits, const u64 *__restrict__ hit_base,
 								 const u32 *__restrict__ hit_cnt, const uint4 *__restrict__ units,
@@ -543,6 +746,7 @@ __global__ void __launch_bounds__(THREADS) hit_reduce_kernel(const u64 *__restri
 	u32 *s_count = s_tag + (size_t) HP * WAYS;                           // [HP * WAYS]
 	u64 *s_okey = reinterpret_cast<u64 *>(s_count + (size_t) HP * WAYS); // [HR_OVF] pairs whose halo ran out of ways: open addressing on the record
 	u32 *s_ocnt = reinterpret_cast<u32 *>(s_okey + HR_OVF);              // [HR_OVF]
+	u64 *s_queue = reinterpret_cast<u64 *>(s_ocnt + HR_OVF);             // [THREADS / 32][HR_QCAP]
 	__shared__ u32 s_warpsum[THREADS / 32];
 	__shared__ u64 s_base;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -557,10 +761,52 @@ __global__ void __launch_bounds__(THREADS) hit_reduce_kernel(const u64 *__restri
 	__syncthreads();
 	const u64 *src = hits + hit_base[d];
 	const u32 tag_mask = (u32) ((1ull << hp.rec_a_shift) - 1ull);
+	const int ash = hp.rec_a_shift;
 	u32 spilled = 0;
 	bool ovf = false;           // record buffer full (cause 16)
+	u64 *queue = s_queue + (size_t) warp * HR_QCAP;
+	u32 qn = 0;                 // entries on the warp's queue (same in all its lanes)
+	const u32 lt = lanemask_lt();
+	// slow path for one record per lane: claim a way, else the overflow table, else straight to the output
+	auto slow = [&](u64 rec) {
+		const u32 a = (u32) (rec >> ash) & (HP - 1u);
+		const u32 tag = (u32) rec & tag_mask;
+		u32 *tg = s_tag + (size_t) a * WAYS;
+		int w = -1;
+#pragma unroll
+		for (int x = 0; x < WAYS; x++) {
+			u32 cur = *reinterpret_cast<volatile u32 *>(tg + x);
+			if (cur == HIT_EMPTY) {
+				cur = atomicCAS(tg + x, HIT_EMPTY, tag);
+				if (cur == HIT_EMPTY) cur = tag;
+			}
+			if (cur == tag) { w = x; break; }
+		}
+		if (w >= 0) { atomicAdd(s_count + (size_t) a * WAYS + w, 1u); return; }
+		u32 h = __umulhi((u32) ((rec * 0x9E3779B97F4A7C15ull) >> 32), (u32) HR_OVF);
+		int probe = 0;
+		for (; probe < HR_OVF_PROBES; probe++) {
+			u64 cur = *reinterpret_cast<volatile u64 *>(s_okey + h);
+			if (cur == ~0ull) {
+				cur = atomicCAS((unsigned long long *) (s_okey + h), ~0ull, (unsigned long long) rec);
+				if (cur == ~0ull) cur = rec;
+			}
+			if (cur == rec) { atomicAdd(s_ocnt + h, 1u); break; }
+			h = h + 1 == HR_OVF ? 0u : h + 1;
+		}
+		if (probe == HR_OVF_PROBES) {
+			// last resort: a (record, 1) pair straight to the output
+			const u64 o = atomicAdd((unsigned long long *) &counters[2], 1ull);
+			if (o < rec_cap) { rec_key[o] = rec; rec_cnt[o] = 1u; }
+			else ovf = true;
+		}
+		spilled++;
+	};
 	constexpr int UNR = 8;                      // loads in flight per thread (4: 2.7 ms, 8: 2.4 ms, 16: 2.9 ms)
-	for (u64 j0 = lo + tid; j0 < hi; j0 += (u64) THREADS * UNR) {
+	const u64 span = hi > lo ? hi - lo : 0;
+	const u64 iters = (span + (u64) THREADS * UNR - 1) / ((u64) THREADS * UNR);           // same for all threads: whole warps stay in the loop
+	for (u64 it = 0; it < iters; it++) {
+		const u64 j0 = lo + it * (u64) THREADS * UNR + tid;
 		u64 r[UNR];
 #pragma unroll
 		for (int q = 0; q < UNR; q++) {
@@ -569,58 +815,37 @@ __global__ void __launch_bounds__(THREADS) hit_reduce_kernel(const u64 *__restri
 		}
 #pragma unroll
 		for (int q = 0; q < UNR; q++) {
-			if (r[q] == ~0ull) continue;
-			const u32 ap = (u32) (r[q] >> hp.rec_a_shift);                  // halo; its low log_hp bits index the partition
-			if (SUB && ((ap >> hp.log_hs) & ((1u << sub_log) - 1u)) != sub) continue;
+			const u32 ap = (u32) (r[q] >> ash);                             // halo; its low log_hp bits index the partition
+			bool valid = r[q] != ~0ull;
+			if (SUB) valid = valid && ((ap >> hp.log_hs) & ((1u << sub_log) - 1u)) == sub;
 			const u32 a = ap & (HP - 1u);
 			const u32 tag = (u32) r[q] & tag_mask;
-			u32 *tg = s_tag + (size_t) a * WAYS;
 			int w = -1;
-			bool has_empty = true;                                       // ways only ever go from empty to taken
 			if (WAYS == 4) {
-				const uint4 t4 = *reinterpret_cast<const uint4 *>(tg);
+				const uint4 t4 = *reinterpret_cast<const uint4 *>(s_tag + (size_t) a * 4);
 				w = t4.x == tag ? 0 : t4.y == tag ? 1 : t4.z == tag ? 2 : t4.w == tag ? 3 : -1;
-				has_empty = t4.w == HIT_EMPTY || t4.z == HIT_EMPTY || t4.y == HIT_EMPTY || t4.x == HIT_EMPTY;
-			} else if (WAYS == 2) {
-				const uint2 t2 = *reinterpret_cast<const uint2 *>(tg);
+			} else {
+				const uint2 t2 = *reinterpret_cast<const uint2 *>(s_tag + (size_t) a * 2);
 				w = t2.x == tag ? 0 : t2.y == tag ? 1 : -1;
-				has_empty = t2.y == HIT_EMPTY || t2.x == HIT_EMPTY;
 			}
-			if (w < 0 && has_empty) {
-				// first sight of this partner (or a race with its first sight): claim an empty way
-#pragma unroll
-				for (int x = 0; x < WAYS; x++) {
-					u32 cur = *reinterpret_cast<volatile u32 *>(tg + x);
-					if (cur == HIT_EMPTY) {
-						cur = atomicCAS(tg + x, HIT_EMPTY, tag);
-						if (cur == HIT_EMPTY) cur = tag;
-					}
-					if (cur == tag) { w = x; break; }
+			if (valid && w >= 0) atomicAdd(s_count + (size_t) a * WAYS + w, 1u);
+			const bool pend = valid && w < 0;
+			const u32 bq = __ballot_sync(0xffffffffu, pend);
+			if (bq) {
+				if (pend) queue[qn + __popc(bq & lt)] = r[q];
+				qn += __popc(bq);
+				if (qn >= 32) {
+					__syncwarp();
+					qn -= 32;
+					const u64 rec = queue[qn + lane];
+					__syncwarp();
+					slow(rec);
 				}
-			}
-			if (w >= 0) atomicAdd(s_count + (size_t) a * WAYS + w, 1u);
-			else {
-				u32 h = (u32) ((r[q] * 0x9E3779B97F4A7C15ull) >> 52) & (HR_OVF - 1);
-				int probe = 0;
-				for (; probe < HR_OVF_PROBES; probe++) {       // (left to the compiler: forcing this loop to stay rolled made the kernel 5x slower)
-					u64 cur = *reinterpret_cast<volatile u64 *>(s_okey + h);
-					if (cur == ~0ull) {
-						cur = atomicCAS((unsigned long long *) (s_okey + h), ~0ull, (unsigned long long) r[q]);
-						if (cur == ~0ull) cur = r[q];
-					}
-					if (cur == r[q]) { atomicAdd(s_ocnt + h, 1u); break; }
-					h = (h + 1) & (HR_OVF - 1);
-				}
-				if (probe == HR_OVF_PROBES) {
-					// last resort: a (record, 1) pair straight to the output
-					const u64 o = atomicAdd((unsigned long long *) &counters[2], 1ull);
-					if (o < rec_cap) { rec_key[o] = r[q]; rec_cnt[o] = 1u; }
-					else ovf = true;
-				}
-				spilled++;
 			}
 		}
 	}
+	__syncwarp();
+	if ((u32) lane < qn) slow(queue[lane]);
 	__syncthreads();
 	// emit the live ways + the overflow list
 	u32 live = 0;
@@ -746,7 +971,7 @@ template <int WAYS, bool SUB, int THREADS>
 static int launch_reduce(metro_ctx *ctx, const HitPlan &hp, const u64 *hits, const u64 *hit_base, const u32 *hit_cnt, const uint4 *units, const u32 *n_units,
 			 u64 *rec_key, u32 *rec_cnt, u64 rec_cap, u32 *ovf)
 {
-	const size_t smem = ((size_t) WAYS << hp.log_hs) * 8 + (size_t) HR_OVF * 12;
+	const size_t smem = ((size_t) WAYS << hp.log_hs) * 8 + (size_t) HR_OVF * 12 + (size_t) (THREADS / 32) * HR_QCAP * 8;
 	CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<WAYS, SUB, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	hit_reduce_kernel<WAYS, SUB, THREADS><<<HR_MAX_UNITS << (hp.log_hp - hp.log_hs), THREADS, smem, ctx->stream>>>(hits, hit_base, hit_cnt, units, n_units, hp, rec_key, rec_cnt, rec_cap,
 										   ctx->counters.as<u64>(), ovf);
@@ -771,12 +996,14 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	const u64 nbk = 1ull << (P.b1 + P.b2);                                 // buckets per catalogue
 	const u64 nb1 = 2 * (1ull << P.b1) * P.r1, nb = 2 * nbk;                // level-1 regions, final buckets (both catalogues)
 	const HitPlan hp = make_hit_plan(rec_halo_bits, L.type_bits, c0.n_halos);
-	const u64 hits_cap = 2ull * ((u64) c0.n_tuples + (u64) HIST_SAMPLE * PT_TILE) + (u64) (hp.slack + 2) * hp.nbh;
+	// 2 hits per catalogue-0 tuple + the per-range slack; the tuple counts are sampled (every HIST_SAMPLE-th tile, scaled) by up to two
+	// streams (resident part: hit_hist_kernel; the rest: pass A), each over-estimating by up to HIST_SAMPLE tiles
+	const u64 hits_cap = 2ull * ((u64) c0.n_tuples + 2ull * HIST_SAMPLE * PT_TILE) + (u64) (hp.slack + 2) * hp.nbh;
 	const u64 rec_cap = 16ull * (u64) (c0.n_halos + c1.n_halos) + (1ull << 20);
 	int rc;
 	// keys_a: level-1 regions, dead after pass B and reused for the hit regions
-	if ((rc = dev_reserve(ctx, ctx->keys_a, std::max((size_t) nb1 * P.cap1, (size_t) hits_cap) * 8 + 64))) return rc;
-	if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) nb * P.cap2 * 8 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->keys_a, (std::max((size_t) nb1 * P.cap1, (size_t) hits_cap) + PT_TILE) * 8 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->keys_b, ((size_t) nb * P.cap2 + PT_TILE) * 8 + 64))) return rc;
 	if ((rc = dev_reserve(ctx, ctx->scratch[0], (size_t) rec_cap * sizeof(u64)))) return rc;
 	if ((rc = dev_reserve(ctx, ctx->scratch[1], (size_t) rec_cap * sizeof(u32)))) return rc;
 	// small state: [g1 nb1*CSTRIDE][hit_cnt 1024*CSTRIDE][t0 1024*CSTRIDE][g2 nb][hit_cap 1024][ovf, n_units, pad..16] u32, then hit_base u64[1024],
@@ -814,8 +1041,8 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 		if ((rc = launch_part<true>(ctx, P.b1, (unsigned) div_up<i64>(cnt, PT_TILE), c.d_pid() + first, c.d_halo() + first, c.d_type() ? c.d_type() + first : nullptr,
 					    (u64) cnt, (u32) (s == 0 ? half0 : half1), L, P, ctx->keys_a.as<u64>(), nullptr, g1, ovf, s == 0 ? t0 : nullptr, hp))) return rc;
 	}
-	// hit regions: exact catalogue-0 tuple count per halo range (counted by pass A) -> capacity and base
-	hit_plan_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(t0, hp.nbh, hp.slack, hit_base, hit_cap);
+	// hit regions: sampled catalogue-0 tuple count per halo range (pass A / hit_hist_kernel) -> capacity and base
+	hit_plan_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(t0, hp.nbh, hp.slack, hits_cap, hit_base, hit_cap, ovf);
 	CUDA_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
@@ -825,16 +1052,27 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
 	// pass C
 	{
-		CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BJ_SMEM));
 		// test hook: a smaller staging capacity for the default bucket size forces the finer-bucket retry
 		static const u32 test_wcap = getenv("METRO_TEST_WCAP") ? (u32) atoi(getenv("METRO_TEST_WCAP")) : 0u;
+		static const bool no_direct = getenv("METRO_NO_DIRECT") && atoi(getenv("METRO_NO_DIRECT"));
 		const u32 wcap = (test_wcap && !finer_plan) ? std::min<u32>(test_wcap, BJ_WCAP) : (u32) BJ_WCAP;
 		const int rb = L.pid_bits - P.b1 - P.b2;
-		const u64 rmask = rb >= 64 ? ~0ull : ((1ull << rb) - 1ull);
 		const u64 *kb = ctx->keys_b.as<u64>();
-		bucket_join_kernel<<<(unsigned) nbk, BJ_THREADS, BJ_SMEM, st>>>(kb + (size_t) half0 * nbk * P.cap2, kb + (size_t) half1 * nbk * P.cap2, g2 + (size_t) half0 * nbk,
-										g2 + (size_t) half1 * nbk, P.cap2, L, rmask, hp, hit_base, hit_cap, hit_cnt,
-										ctx->keys_a.as<u64>(), counters, ovf, wcap);
+		if (!no_direct && rb <= BD_MAX_RB && L.snap_shift <= 30) {
+			// few residual pid bits (dense IDs): direct-address table
+			const size_t smem = bd_smem_bytes(rb);
+			CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+			bucket_join_direct_kernel<<<(unsigned) nbk, BJ_THREADS, smem, st>>>(kb + (size_t) half0 * nbk * P.cap2, kb + (size_t) half1 * nbk * P.cap2,
+											    g2 + (size_t) half0 * nbk, g2 + (size_t) half1 * nbk, P.cap2, L, rb < 2 ? 2 : rb,
+											    (u32) bd_front_bytes(rb < 2 ? 2 : rb), hp, hit_base, hit_cap, hit_cnt,
+											    ctx->keys_a.as<u64>(), counters, ovf, wcap);
+		} else {
+			CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BJ_SMEM));
+			const u64 rmask = rb >= 64 ? ~0ull : ((1ull << rb) - 1ull);
+			bucket_join_kernel<<<(unsigned) nbk, BJ_THREADS, BJ_SMEM, st>>>(kb + (size_t) half0 * nbk * P.cap2, kb + (size_t) half1 * nbk * P.cap2, g2 + (size_t) half0 * nbk,
+											g2 + (size_t) half1 * nbk, P.cap2, L, rmask, hp, hit_base, hit_cap, hit_cnt,
+											ctx->keys_a.as<u64>(), counters, ovf, wcap);
+		}
 		CUDA_TRY(ctx, cudaGetLastError());
 		ctx->launches++;
 	}

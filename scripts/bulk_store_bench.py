@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd())
 import torch
 import metrocpp_b200 as mb
 eng = mb.MetroEngine(0)
-lib = eng.lib
+lib = C.CDLL(os.path.join(os.path.dirname(mb.__file__), "libmetro_b200_bench.so"))      # micro-benchmarks live outside the product ABI
 lib.metro_bulk_store_bench.restype = C.c_int
 out = torch.empty(1 << 30, dtype=torch.int64, device="cuda")      # 8 GB
 ms = C.c_float()

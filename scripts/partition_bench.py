@@ -3,7 +3,7 @@ sys.path.insert(0, os.getcwd())
 import numpy as np, torch
 import metrocpp_b200 as mb
 eng = mb.MetroEngine(0)
-lib = eng.lib
+lib = C.CDLL(os.path.join(os.path.dirname(mb.__file__), "libmetro_b200_bench.so"))      # micro-benchmarks live outside the product ABI
 lib.metro_partition_bench.restype = C.c_int
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000_000
 g = torch.Generator(device="cuda"); g.manual_seed(1)

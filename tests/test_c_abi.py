@@ -29,6 +29,15 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in _lib.load().metro_version()
 
 
+def test_library_exports_nothing_undeclared():
+    """The product ABI is exactly include/metro_b200.h: no extra extern "C" metro_* entry point (benchmarks live in
+    libmetro_b200_bench.so)."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = sorted({ln.split()[-1] for ln in out.splitlines() if re.match(r".* T metro_[a-z0-9_]+$", ln)})
+    assert exported == declared_symbols()
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
