@@ -287,6 +287,65 @@ def run_reference_arm(args, rank):
 
 
 # --------------------------------------------------------------------------------------------
+def sharded_parity_check(eng, rank, world, dist, dev):
+    """N>1 only, before anything is timed: a small pair (1500 halos, 2.5e5 tuples per snapshot) sharded by particle-ID range over
+    the same ranks, communicator and front end as the benchmark, its concatenated per-rank trees, tokens and shifted catalogue
+    compared bit for bit with the C oracle on the unsharded data (the checker; never timed).  Raises on any mismatch."""
+    import numpy as np
+    import metrocpp_b200 as mb
+    prm = mb.make_params(nptypes=2, max_orphan_steps=5, flavour=mb.FLAVOUR_GATHER)
+    bits = 20
+    spec = mb.SynthSpec(seed=31, n_halos=1500, n_tuples=250_000, pid_bits=bits, shard=0, n_shards=1)
+    c0, c1 = mb.synth_pair_host(prm, spec, 0), mb.synth_pair_host(prm, spec, 1)
+    c0.type = None; c1.type = None
+    per = (1 << bits) // world
+    lo, hi = per * rank, (1 << bits) + 1 if rank == world - 1 else per * (rank + 1)
+
+    def shard(c):
+        m = (c.pid >= lo) & (c.pid < hi)
+        return mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, c.pid[m], c.halo[m], None)
+    eng.upload(0, prm, shard(c0))
+    eng.upload(1, prm, shard(c1))
+    res = eng.find_progenitors_and_clean(prm)
+    path = eng.timings()["path"]
+    eng.shift_halos_parts(prm)
+    d0 = eng.fetch_catalogue(0)
+    mine = {"tree_main": res.tree_main, "tree_orphan": res.tree_orphan, "tree_off": res.tree_off, "clean_prog": res.clean_prog,
+            "clean_ncommon": res.clean_ncommon, "token": res.token_halo, "n_hits": res.info["n_hits"], "raw_prog0": res.raw_prog[0],
+            "raw_merit0": res.raw_merit[0], "shift": (d0.halo_id, d0.is_token, d0.pid, d0.halo), "path": path}
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    out = {"world": world, "ok": True, "front_end": "partition join" if path == 1 else "LSD sort", "halos": 1500,
+           "tuples": int(c0.n_tuples + c1.n_tuples)}
+    if rank == 0:
+        from oracle import binding
+        from tests.helpers import to_oracle_catalogue
+        oprm = binding.Params(2, prm.min_part_cmp, prm.min_part_halo, prm.fac_orphan_steps, prm.max_orphan_steps, 0)
+        o0, o1 = to_oracle_catalogue(c0), to_oracle_catalogue(c1)
+        ores = binding.match_pair(oprm, o0, o1)
+        cat = lambda k: np.concatenate([p[k] for p in parts])
+        counts = np.concatenate([np.diff(p["tree_off"]) for p in parts])
+        checks = [(cat("tree_main"), ores.tree_main), (cat("tree_orphan"), ores.tree_orphan), (np.concatenate([[0], np.cumsum(counts)]), ores.tree_off),
+                  (cat("clean_prog"), ores.clean_prog), (cat("clean_ncommon"), ores.clean_ncommon), (cat("raw_prog0"), ores.raw_prog[0]),
+                  (cat("raw_merit0"), ores.raw_merit[0])]
+        for p in parts:
+            checks.append((p["token"], ores.token_halo))
+            checks.append((np.array([p["n_hits"]]), np.array([ores.n_hits])))
+        exp = binding.shift(oprm, o0, o1, ores.token_halo)
+        for p in parts:
+            checks.append((p["shift"][0], exp.halo_id)); checks.append((p["shift"][1], exp.is_token))
+        H = np.uint64(exp.n_halos)
+        got = np.sort(np.concatenate([p["shift"][2] * H + p["shift"][3].astype(np.uint64) for p in parts]))
+        checks.append((got, np.sort(exp.pid * H + exp.halo.astype(np.uint64))))
+        out["ok"] = bool(all(a.shape == b.shape and np.array_equal(a, b) for a, b in checks))
+        out["trees"] = int(ores.tree_main.shape[0]); out["tokens"] = int(ores.token_halo.shape[0]); out["checked_arrays"] = len(checks)
+    flag = [out["ok"]]
+    dist.broadcast_object_list(flag, src=0, device=dev)
+    if not flag[0]:
+        raise RuntimeError(f"sharded parity check against the oracle FAILED at world={world}")
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -306,13 +365,17 @@ def run_ours(args, rank, world, local_rank):
     prm = mb.make_params(nptypes=2, min_part_cmp=10, min_part_halo=100, fac_orphan_steps=100, max_orphan_steps=15,
                          flavour=mb.FLAVOUR_GATHER)          # config/fullbox_*.cfg settings
     spec = mb.SynthSpec(seed=20261019, n_halos=H_glob, n_tuples=N_glob, pid_bits=pid_bits, shard=rank, n_shards=world)
+    if world > 1:
+        os.environ.setdefault("METRO_PART_MIN_N", "20000")     # the parity pair is small: send it through the benchmarked front end too
     eng = mb.MetroEngine(local_rank)
     stream = torch.cuda.current_stream(dev)
     eng.set_stream(stream.cuda_stream)
+    parity = None
     if world > 1:
         uid = [eng.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0, device=dev)
         eng.comm_init(rank, world, uid[0])
+        parity = sharded_parity_check(eng, rank, world, dist, dev)
     eng.synth_pair_device(prm, spec)
     if world > 1:
         # catalogue npart of the earlier halos = sum over the pid shards
@@ -433,6 +496,8 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
+    if parity:
+        line["parity_check"] = parity
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -544,32 +544,49 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, u32
 // them are bound) leave rb <= 14: the catalogue-1 members of the bucket then sit in a DIRECT-ADDRESS table tab[2^rb] of 32-bit
 // payloads ((halo, type) + 1; 0 = empty): no hash, no tag compare, a probe is one 4-byte shared-memory load.  Second and later
 // members of a particle (it is listed under a subhalo and under its host) hang off the slot as a chain of (payload, next) nodes.
-// The catalogue-1 keys of the bucket arrive through 1-D bulk copies (TMA) into the hit staging area, which is idle until the probe:
-// no load instructions, no address arithmetic and no register staging on the build side, and the copies fly while the table is cleared.
+//
+// Because a probe is that cheap it runs TWICE, and the hits are never staged: every thread keeps its catalogue-0 keys in registers;
+// sweep 1 only counts (chain length -> one shared-memory add per KEY on the counter of its hit partition, the returned value is the
+// key's rank inside the partition); the partition counts are scanned and the space in the global hit regions reserved; sweep 2 walks
+// the chains again and drops every hit record at its final place in the partition-sorted buffer, which is then written out in runs.
+// No warp ballots, no per-hit counting or scattering passes, five block barriers per bucket.
+//
+// The catalogue-1 keys of the bucket arrive through 1-D bulk copies (TMA) into the sorted buffer, which is idle until sweep 2: no
+// load instructions, address arithmetic or register staging on the build side, and the copies fly while the table is cleared.
 #define BD_NODES 1024           // chain nodes per bucket
 #define BD_FLAG 0x80000000u     // slot / next holds a node index, not a payload
-#define BD_U 4                  // catalogue-0 keys per thread and probe batch
-#define BD_CHUNK 1024           // keys per bulk copy == keys one build sweep of the CTA consumes
-#define BD_MAXCHUNK 6           // BJ_SH / BD_CHUNK
-#define BD_MAX_RB 14             // 64 KB table (one CTA per SM); 13 bits and less: two CTAs per SM
-static size_t bd_front_bytes(int rb) { return std::max(((size_t) 4 << rb) + (size_t) BD_NODES * 8, (size_t) BJ_SH * 8); }
-static size_t bd_smem_bytes(int rb) { return bd_front_bytes(rb) + (size_t) BJ_SH * 8 + (size_t) HIT_MAX_PARTS * 12; }
+#define BD_KPT BJ_KPT           // catalogue-0 keys per thread (all held in registers): cap2 <= BJ_THREADS * BD_KPT
+#define BD_CHUNK 2048           // keys per bulk copy == keys one build sweep of the CTA consumes (4 per thread)
+#define BD_MAXCHUNK 3           // BJ_SH / BD_CHUNK
+#define BD_MAX_RB 14            // 64 KB table (one CTA per SM); 13 bits and less: two CTAs per SM
+static size_t bd_table_bytes(int rb) { return ((size_t) 4 << rb) + (size_t) BD_NODES * 8; }
+static size_t bd_smem_bytes(int rb) { return bd_table_bytes(rb) + (size_t) BJ_SH * 8 + (size_t) HIT_MAX_PARTS * 16; }
+
+__device__ __forceinline__ void bd_insert(u32 *tab, uint2 *nodes, u32 *s_nnodes, u32 r, u32 p, u32 old, u32 &ovf)
+{
+	if (old != 0u) {                                                     // the particle has a member already: chain this one in front
+		const u32 i = atomicAdd(s_nnodes, 1u);
+		if (i < BD_NODES) nodes[i] = make_uint2(p, atomicExch(&tab[r], BD_FLAG | i));
+		else ovf |= 2u;
+	}
+}
 
 __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_direct_kernel(const u64 *__restrict__ keys0, const u64 *__restrict__ keys1,
 									   const u32 *__restrict__ gcount0, const u32 *__restrict__ gcount1, u64 cap2,
-									   KeyLayout L, int rb, u32 front_bytes, HitPlan hp, const u64 *__restrict__ hit_base,
+									   KeyLayout L, int rb, HitPlan hp, const u64 *__restrict__ hit_base,
 									   const u32 *__restrict__ hit_cap, u32 *hit_cnt, u64 *__restrict__ hits_out,
-									   u64 *counters, u32 *overflow, u32 wcap /* staging slots per warp, <= BJ_WCAP */)
+									   u64 *counters, u32 *overflow, u32 hcap /* hits a bucket may produce, <= BJ_SH */,
+									   u32 pf_dist, u32 pf_bytes0, u32 pf_bytes1)
 {
 	extern __shared__ __align__(128) unsigned char dsm[];
 	u32 *tab = reinterpret_cast<u32 *>(dsm);                             // [2^rb] direct-address slots
 	uint2 *nodes = reinterpret_cast<uint2 *>(tab + (1u << rb));          // [BD_NODES] (payload, next)
-	u64 *sorted = reinterpret_cast<u64 *>(dsm);                          // after the probe: [BJ_SH] hits sorted by partition (table and nodes are dead)
-	u64 *stage = reinterpret_cast<u64 *>(dsm + front_bytes);             // [BJ_SH] build: catalogue-1 keys (TMA destination); probe: hits in discovery order
-	i64 *s_dst = reinterpret_cast<i64 *>(stage + BJ_SH);                 // [HIT_MAX_PARTS]
-	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + HIT_MAX_PARTS);        // [HIT_MAX_PARTS]
+	u64 *sorted = reinterpret_cast<u64 *>(nodes + BD_NODES);             // [BJ_SH] build: catalogue-1 keys (TMA destination); sweep 2: hits sorted by partition
+	i64 *s_dst = reinterpret_cast<i64 *>(sorted + BJ_SH);                // [HIT_MAX_PARTS] global slot of a partition's run minus its local start
+	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + HIT_MAX_PARTS);        // [HIT_MAX_PARTS] hits per partition
+	u32 *s_start = s_cnt + HIT_MAX_PARTS;                                // [HIT_MAX_PARTS] local start of a partition in the sorted buffer
 	__shared__ __align__(8) u64 s_bar[BD_MAXCHUNK];
-	__shared__ u32 s_nnodes, s_wcount[BJ_THREADS / 32], s_warpsum[BJ_THREADS / 32];
+	__shared__ u32 s_nnodes, s_warpsum[BJ_THREADS / 32];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const u64 g = blockIdx.x;
 	const u32 n0 = gcount0[g], n1 = gcount1[g];
@@ -584,107 +601,132 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_direct_kernel(const
 			const u32 have = n1 - c * BD_CHUNK < BD_CHUNK ? n1 - c * BD_CHUNK : BD_CHUNK;
 			const u32 bytes = ((have + 1) & ~1u) * 8;                  // whole 16-byte units (cap2 is even: the pad key is inside the bucket)
 			mbar_expect_tx(&s_bar[c], bytes);
-			tma_load_1d(stage + c * BD_CHUNK, src1 + c * BD_CHUNK, bytes, &s_bar[c]);
+			tma_load_1d(sorted + c * BD_CHUNK, src1 + c * BD_CHUNK, bytes, &s_bar[c]);
 		}
 	}
-	// the first probe batch is requested now and used after the build
-	u64 kn[BD_U];
+	// the buckets a later CTA of this SM will join are pulled into L2 now (blocks start in index order)
+	if (tid == 32 && pf_dist && g + pf_dist < gridDim.x) {
+		asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src0 + (u64) pf_dist * cap2), "r"(pf_bytes0) : "memory");
+		asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src1 + (u64) pf_dist * cap2), "r"(pf_bytes1) : "memory");
+	}
+	// the catalogue-0 members: requested now, used after the build, kept in registers until the end
+	u64 k[BD_KPT];
 #pragma unroll
-	for (int u = 0; u < BD_U; u++) {
-		const u32 j = u * BJ_THREADS + tid;
-		kn[u] = j < n0 ? ld_stream_u64(src0 + j) : 0ull;
+	for (int i = 0; i < BD_KPT; i++) {
+		const u32 j = i * BJ_THREADS + tid;
+		k[i] = j < n0 ? ld_stream_u64(src0 + j) : 0ull;
 	}
 	{
 		uint4 *t4 = reinterpret_cast<uint4 *>(tab);
 		for (u32 i = tid; i < (1u << rb) / 4; i += BJ_THREADS) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+		for (u32 i = tid; i < HIT_MAX_PARTS; i += BJ_THREADS) s_cnt[i] = 0;
 	}
-	u32 ovf = 0;                // overflow causes: 2 table (chain nodes) full, 4 hit staging full, 8 hit region full
+	u32 ovf = 0;                // overflow causes: 2 table (chain nodes) full, 4 more hits than the sorted buffer holds, 8 hit region full
 	__syncthreads();
 	const u32 rmask = (1u << rb) - 1u;
 	const u32 lowmask = (1u << L.snap_shift) - 1u;                       // (halo, type) of a key
 	const int psft = L.pid_shift;
-	// build
+	// build: 4 keys per thread and sweep, all four compare-and-swaps in flight before any result is looked at
 #pragma unroll 1
 	for (u32 c = 0; c < nchunk; c++) {
 		mbar_wait(&s_bar[c], 0);
-		const u32 j = c * BD_CHUNK + 2 * tid;
-		const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(stage + j);
-		// both compare-and-swaps are issued before either result is looked at
-		u32 r[2], p[2], old[2];
+		const u32 j = c * BD_CHUNK + 4 * tid;
+		const ulonglong2 ka = *reinterpret_cast<const ulonglong2 *>(sorted + j), kb = *reinterpret_cast<const ulonglong2 *>(sorted + j + 2);
+		const u64 kk[4] = {ka.x, ka.y, kb.x, kb.y};
+		u32 r[4], p[4], old[4];
 #pragma unroll
-		for (int q = 0; q < 2; q++) {
-			const u64 k = q ? kk.y : kk.x;
-			r[q] = (u32) (k >> psft) & rmask;
-			p[q] = ((u32) k & lowmask) + 1u;
+		for (int q = 0; q < 4; q++) {
+			r[q] = (u32) (kk[q] >> psft) & rmask;
+			p[q] = ((u32) kk[q] & lowmask) + 1u;
 		}
 #pragma unroll
-		for (int q = 0; q < 2; q++) old[q] = j + q < n1 ? atomicCAS(&tab[r[q]], 0u, p[q]) : 0u;
+		for (int q = 0; q < 4; q++) old[q] = j + q < n1 ? atomicCAS(&tab[r[q]], 0u, p[q]) : 0u;
 #pragma unroll
-		for (int q = 0; q < 2; q++) {
-			if (old[q] != 0u) {                                          // the particle has a member already: chain this one in front
-				const u32 i = atomicAdd(&s_nnodes, 1u);
-				if (i < BD_NODES) nodes[i] = make_uint2(p[q], atomicExch(&tab[r[q]], BD_FLAG | i));
-				else ovf |= 2u;
-			}
-		}
+		for (int q = 0; q < 4; q++) bd_insert(tab, nodes, &s_nnodes, r[q], p[q], old[q], ovf);
 	}
-	__syncthreads();                                                     // table complete; the staging area is free for the hits
-	// probe: every member of the slot's chain is one hit
+	__syncthreads();                                                     // table complete; the sorted buffer is free
 	const int tb = L.type_bits;
 	const u32 tmask = L.type_mask;
-	const u32 wbase = (u32) warp * BJ_WCAP;
-	u32 wpos = 0;                                                        // hits staged by this warp so far (same in all its lanes)
-	const u32 lt = lanemask_lt();
-#pragma unroll 1
-	for (u32 j0 = 0; j0 < n0; j0 += BD_U * BJ_THREADS) {
-		u64 k[BD_U];
-		u32 v[BD_U];
+	const int dsh = tb + hp.log_hp;                                       // key -> hit partition of its halo
+	const u32 dmask = L.halo_mask >> hp.log_hp;
+	// sweep 1: hits per key (its chain length) -> counter of the key's partition; the value returned is the key's rank there
+	u32 rank[BD_KPT];
 #pragma unroll
-		for (int u = 0; u < BD_U; u++) {
-			k[u] = kn[u];
-			const u32 jn = j0 + (BD_U + u) * BJ_THREADS + tid;
-			kn[u] = jn < n0 ? ld_stream_u64(src0 + jn) : 0ull;
+	for (int i = 0; i < BD_KPT; i++) {
+		const u32 v = tab[(u32) (k[i] >> psft) & rmask];                  // (a key past the end is 0: slot 0 is read and ignored)
+		u32 len = v != 0u ? 1u : 0u;
+		if (v & BD_FLAG) {
+			u32 nx = nodes[v & ~BD_FLAG].y;
+			len = 2u;
+			while (nx & BD_FLAG) { nx = nodes[nx & ~BD_FLAG].y; len++; }
 		}
+		rank[i] = 0;
+		if (i * BJ_THREADS + tid < n0 && len) rank[i] = atomicAdd(&s_cnt[((u32) k[i] >> dsh) & dmask], len);
+	}
+	__syncthreads();
+	// exclusive scan of the partition counts (2 per thread); region space reserved with one global atomic per partition
+	constexpr int BPT = HIT_MAX_PARTS / BJ_THREADS;
+	u32 loc[BPT], sum = 0;
 #pragma unroll
-		for (int u = 0; u < BD_U; u++) {                                 // (a key past the end is 0: slot 0 is read and ignored)
-			const u32 t = tab[(u32) (k[u] >> psft) & rmask];
-			v[u] = j0 + u * BJ_THREADS + tid < n0 ? t : 0u;
-		}
+	for (int q = 0; q < BPT; q++) { const u32 b = tid * BPT + q; loc[q] = b < hp.nbh ? s_cnt[b] : 0u; sum += loc[q]; }
+	u32 incl = sum;
 #pragma unroll
-		for (int u = 0; u < BD_U; u++) {
-			u32 p1 = v[u], p2 = 0, rest = 0;
-			if (p1 & BD_FLAG) { const uint2 nd = nodes[p1 & ~BD_FLAG]; p1 = nd.x; rest = nd.y; }
-			if (rest) {
-				if (rest & BD_FLAG) { const uint2 nd = nodes[rest & ~BD_FLAG]; p2 = nd.x; rest = nd.y; }
-				else { p2 = rest; rest = 0; }
+	for (int off = 1; off < 32; off <<= 1) {
+		const u32 x = __shfl_up_sync(0xffffffffu, incl, off);
+		if (lane >= off) incl += x;
+	}
+	if (lane == 31) s_warpsum[warp] = incl;
+	__syncthreads();
+	u32 pre = 0, nh = 0;
+#pragma unroll
+	for (int w = 0; w < BJ_THREADS / 32; w++) { const u32 x = s_warpsum[w]; pre += (w < warp) ? x : 0u; nh += x; }
+	if (nh > hcap) {                                                     // more hits than the buffer holds (same decision in every thread)
+		if (tid == 0) atomicOr(overflow, 4u | ovf);
+		return;
+	}
+	u32 run = pre + incl - sum;
+#pragma unroll
+	for (int q = 0; q < BPT; q++) {
+		const u32 b = tid * BPT + q;
+		if (b < hp.nbh) {
+			i64 dst = INT64_MIN;
+			if (loc[q]) {
+				const u32 g0 = atomicAdd(&hit_cnt[b * CSTRIDE], loc[q]);
+				if ((u64) g0 + loc[q] <= (u64) hit_cap[b]) dst = (i64) (hit_base[b] + g0) - (i64) run;
+				else ovf |= 8u;
 			}
-			const u32 kl = (u32) k[u];
-			const u64 recA = ((u64) ((u32) (k[u] >> tb) & L.halo_mask) << hp.rec_a_shift) | (u64) ((kl & tmask) << tb);
-			auto make_rec = [&](u32 p) { const u32 pm = p - 1u; return recA | (u64) (((pm >> tb) << (2 * tb)) | (pm & tmask)); };
-			const u32 b1 = __ballot_sync(0xffffffffu, p1 != 0u), b2 = __ballot_sync(0xffffffffu, p2 != 0u);
-			u32 pos = wpos + __popc(b1 & lt) + __popc(b2 & lt);
-			if (p1) { if (pos < wcap) stage[wbase + pos] = make_rec(p1); pos++; }
-			if (p2) { if (pos < wcap) stage[wbase + pos] = make_rec(p2); }
-			wpos += __popc(b1) + __popc(b2);
-			u32 b3 = __ballot_sync(0xffffffffu, rest != 0u);
-			while (b3) {                                                 // three or more memberships: one lane at a time walks the rest of its chain (rare)
-				const u32 src_lane = __ffs(b3) - 1;
-				b3 &= b3 - 1;
-				u32 extra = 0;
-				if (lane == src_lane) {
-					while (rest) {
-						u32 p;
-						if (rest & BD_FLAG) { const uint2 nd = nodes[rest & ~BD_FLAG]; p = nd.x; rest = nd.y; }
-						else { p = rest; rest = 0; }
-						if (wpos + extra < wcap) stage[wbase + wpos + extra] = make_rec(p);
-						extra++;
-					}
-				}
-				wpos += __shfl_sync(0xffffffffu, extra, src_lane);
-			}
+			s_dst[b] = dst;
+			s_start[b] = run;
+			run += loc[q];
 		}
 	}
-	bj_flush_hits(stage, sorted, s_dst, s_cnt, s_wcount, s_warpsum, wbase, wpos, wcap, hp, hit_base, hit_cap, hit_cnt, hits_out, counters, ovf);
+	if (tid == 0 && nh) atomicAdd((unsigned long long *) &counters[0], (unsigned long long) nh);
+	__syncthreads();
+	// sweep 2: every member of the slot's chain is one hit, written at its final place in the partition-sorted buffer
+#pragma unroll
+	for (int i = 0; i < BD_KPT; i++) {
+		u32 v = i * BJ_THREADS + tid < n0 ? tab[(u32) (k[i] >> psft) & rmask] : 0u;
+		if (v) {
+			const u32 kl = (u32) k[i];
+			const u64 recA = ((u64) ((u32) (k[i] >> tb) & L.halo_mask) << hp.rec_a_shift) | (u64) ((kl & tmask) << tb);
+			u32 pos = s_start[(kl >> dsh) & dmask] + rank[i];
+			do {
+				u32 p;
+				if (v & BD_FLAG) { const uint2 nd = nodes[v & ~BD_FLAG]; p = nd.x; v = nd.y; }
+				else { p = v; v = 0u; }
+				const u32 pm = p - 1u;
+				sorted[pos++] = recA | (u64) (((pm >> tb) << (2 * tb)) | (pm & tmask));
+			} while (v);
+		}
+	}
+	__syncthreads();
+	const int psh = hp.rec_a_shift + hp.log_hp;
+#pragma unroll 4
+	for (u32 j = tid; j < nh; j += BJ_THREADS) {
+		const u64 r = sorted[j];
+		const i64 dst = s_dst[(u32) (r >> psh)];
+		if (dst != INT64_MIN) st_stream_u64(hits_out + dst + (i64) j, r);
+	}
 	if (ovf) atomicOr(overflow, ovf);
 }
 
@@ -732,7 +774,7 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__r
 // small queue (positions from a ballot, no atomics); whenever 32 are queued the warp runs the slow path once with all lanes busy.
 #define HR_QCAP 64              // queue entries per warp: < 32 before a push, <= 32 pushed
 template <int WAYS, bool SUB, int THREADS>
-__global__ void __launch_bounds__(THREADS) hit_reduce_kernel(const u64 *__restrict__ hits, const u64 *__restrict__ hit_base,
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(const u64 *__restrict__ hits, const u64 *__restrict__ hit_base,
 								 const u32 *__restrict__ hit_cnt, const uint4 *__restrict__ units,
 								 const u32 *__restrict__ n_units, HitPlan hp, u64 *__restrict__ rec_key,
 								 u32 *__restrict__ rec_cnt, u64 rec_cap, u64 *counters, u32 *overflow)
@@ -805,13 +847,22 @@ __global__ void __launch_bounds__(THREADS) hit_reduce_kernel(const u64 *__restri
 	constexpr int UNR = 8;                      // loads in flight per thread (4: 2.7 ms, 8: 2.4 ms, 16: 2.9 ms)
 	const u64 span = hi > lo ? hi - lo : 0;
 	const u64 iters = (span + (u64) THREADS * UNR - 1) / ((u64) THREADS * UNR);           // same for all threads: whole warps stay in the loop
+	// software pipeline: the loads of batch it+1 are in flight while batch it is counted
+	u64 rn[UNR];
+#pragma unroll
+	for (int q = 0; q < UNR; q++) {
+		const u64 j = lo + tid + (u64) q * THREADS;
+		rn[q] = j < hi ? ld_stream_u64(src + j) : ~0ull;
+	}
+#pragma unroll 1
 	for (u64 it = 0; it < iters; it++) {
-		const u64 j0 = lo + it * (u64) THREADS * UNR + tid;
+		const u64 j1 = lo + (it + 1) * (u64) THREADS * UNR + tid;
 		u64 r[UNR];
 #pragma unroll
 		for (int q = 0; q < UNR; q++) {
-			const u64 j = j0 + (u64) q * THREADS;
-			r[q] = j < hi ? ld_stream_u64(src + j) : ~0ull;
+			r[q] = rn[q];
+			const u64 j = j1 + (u64) q * THREADS;
+			rn[q] = j < hi ? ld_stream_u64(src + j) : ~0ull;
 		}
 #pragma unroll
 		for (int q = 0; q < UNR; q++) {
@@ -1060,12 +1111,21 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 		const u64 *kb = ctx->keys_b.as<u64>();
 		if (!no_direct && rb <= BD_MAX_RB && L.snap_shift <= 30) {
 			// few residual pid bits (dense IDs): direct-address table
-			const size_t smem = bd_smem_bytes(rb);
+			const int rbk = rb < 2 ? 2 : rb;
+			const size_t smem = bd_smem_bytes(rbk);
+			// L2 prefetch distance in buckets (0 = off) and the bytes to pull per bucket and catalogue (mean fill + 1 sigma, 16-byte units)
+			static const u32 pf_dist = getenv("METRO_C_PREFETCH") ? (u32) atoi(getenv("METRO_C_PREFETCH")) : 320u;
+			u32 pf_b[2];
+			for (int h = 0; h < 2; h++) {
+				const double m = (double) ctx->cat[h == half0 ? 0 : 1].n_tuples / (double) nbk;
+				pf_b[h] = (u32) std::min<u64>(P.cap2 * 8, (((u64) (m + sqrt(m)) + 2) & ~1ull) * 8);
+			}
+			// test hook: a smaller hit capacity for the default bucket size forces the finer-bucket retry
+			const u32 hcap = (test_wcap && !finer_plan) ? std::min<u32>(test_wcap * (BJ_THREADS / 32), BJ_SH) : (u32) BJ_SH;
 			CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 			bucket_join_direct_kernel<<<(unsigned) nbk, BJ_THREADS, smem, st>>>(kb + (size_t) half0 * nbk * P.cap2, kb + (size_t) half1 * nbk * P.cap2,
-											    g2 + (size_t) half0 * nbk, g2 + (size_t) half1 * nbk, P.cap2, L, rb < 2 ? 2 : rb,
-											    (u32) bd_front_bytes(rb < 2 ? 2 : rb), hp, hit_base, hit_cap, hit_cnt,
-											    ctx->keys_a.as<u64>(), counters, ovf, wcap);
+											    g2 + (size_t) half0 * nbk, g2 + (size_t) half1 * nbk, P.cap2, L, rbk, hp, hit_base,
+											    hit_cap, hit_cnt, ctx->keys_a.as<u64>(), counters, ovf, hcap, pf_dist, pf_b[half0], pf_b[half1]);
 		} else {
 			CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) BJ_SMEM));
 			const u64 rmask = rb >= 64 ? ~0ull : ((1ull << rb) - 1ull);
