@@ -402,7 +402,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pass_ms, stage = [], {"pack_hist": 0.0, "sort": 0.0, "join": 0.0, "exchange": 0.0, "select": 0.0}
+    pass_ms, stage = [], {"pack_hist": 0.0, "sort": 0.0, "join": 0.0, "exchange": 0.0, "select": 0.0, "exchange_sendrecv": 0.0}
     launches = 0
     ev0.record(stream)
     for _ in range(args.steps):
@@ -494,6 +494,15 @@ def run_ours(args, rank, world, local_rank):
                                     "partial pair counts -> owner(haloA)/owner(haloB): one grouped ncclSend/ncclRecv all-to-all "
                                     "+ all-reduce(max) of bestDescendant and token flags")},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
+    if world > 1:
+        # NVLink: bytes this rank put on the wire in the grouped send/recv all-to-all over the device time of that group alone
+        # (CUDA events around ncclGroupStart/End; it includes waiting for the slowest peer, so it is a lower bound of the link rate)
+        xb, xms = float(info["exchange_bytes"]), stage["exchange_sendrecv"] / args.steps
+        line["exchange"] = {"bytes_sent_rank0": xb, "ms_sendrecv": xms, "ms_stage": stage["exchange"] / args.steps,
+                            "nvlink_gbs": (xb / (xms * 1e-3) / 1e9) if xms > 0 else None,
+                            "frac_of_900": (xb / (xms * 1e-3) / 1e9 / 900.0) if xms > 0 else None,
+                            "frac_of_measured_770": (xb / (xms * 1e-3) / 1e9 / 770.0) if xms > 0 else None,
+                            "note": "partial pair counts (12 B each) to owner(haloA) and owner(haloB): latency- and skew-bound, not bandwidth-bound"}
     if e2e:
         line["e2e"] = e2e
     if parity:
@@ -535,36 +544,61 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
         off[1:].copy_(torch.cumsum(counts, 0))
         del h_dev, h_sorted, order, counts
         torch.cuda.empty_cache()
-        cats.append((halos, pid, off))
-    h2d = sum(p.numel() * 8 + o.numel() * 8 + c.n_halos * (8 + 4 * prm.nptypes + 4 + 4 + 1) for c, p, o in cats)
+        # IDs as 32-bit offsets from the smallest one when the range allows it (metro_catalogue_upload_csr32): what a reader holds
+        # for a box of up to 1600^3 particles or for one rank's particle-ID range; halves the bytes over the bus
+        pn = pid.numpy().view(np.uint64)
+        base, top = int(pn.min()), int(pn.max())
+        p32 = None
+        if top - base < (1 << 32):
+            p32 = torch.empty(N, dtype=torch.int32, pin_memory=True)
+            np.subtract(pn, np.uint64(base), out=p32.numpy().view(np.uint32), casting="unsafe")
+        cats.append((halos, pid, off, p32, base))
+    narrow = all(c[3] is not None for c in cats)
 
-    def one():
-        for slot, (c, pid, off) in enumerate(cats):
-            hc = mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, pid.numpy().view(np.uint64), None, None)
-            eng.upload(slot, prm, hc, halo_offset=off.numpy())
+    def h2d_bytes(use32):
+        return sum((p32.numel() * 4 if use32 else p.numel() * 8) + o.numel() * 8 + c.n_halos * (8 + 4 * prm.nptypes + 4 + 4 + 1) for c, p, o, p32, _ in cats)
+
+    def one(use32=narrow):
+        for slot, (c, pid, off, p32, base) in enumerate(cats):
+            hc = mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, None if use32 else pid.numpy().view(np.uint64), None, None)
+            if use32:
+                eng.upload(slot, prm, hc, halo_offset=off.numpy(), pid32=p32.numpy().view(np.uint32), pid_base=base)
+            else:
+                eng.upload(slot, prm, hc, halo_offset=off.numpy())
         info = eng.match_pair(prm)
         res = eng.fetch_result(info, raw=False)
         d2h = res.tree_main.nbytes + res.tree_orphan.nbytes + res.tree_off.nbytes + res.clean_prog.nbytes + \
             res.clean_ncommon.nbytes + res.token_halo.nbytes
         return d2h, info
 
-    _, info0 = one()                                        # warm-up (allocations)
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(steps):
-        d2h, info = one()
-    ev1.record(stream)
-    torch.cuda.synchronize(dev)
-    wall = time.perf_counter() - t0
-    ms = max(ev0.elapsed_time(ev1), wall * 1e3)             # host work (packing structs) counts too
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t[0])
+    def timed(n_steps, use32):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(n_steps):
+            d2h, info = one(use32)
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+        wall = time.perf_counter() - t0
+        ms = max(ev0.elapsed_time(ev1), wall * 1e3)         # host work (packing structs) counts too
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms, d2h, info
+
+    one()                                                   # warm-up (allocations)
+    ms, d2h, info = timed(steps, narrow)
+    wide = None
+    if narrow:                                              # the same with full 64-bit IDs over the bus, for reference
+        one(False)
+        ms64, _, _ = timed(1, False)
+        wide = {"ms_per_step": ms64, "value": ids_glob / (ms64 * 1e-3), "h2d_bytes_per_step": int(h2d_bytes(False))}
+        one(narrow)
+    h2d = h2d_bytes(narrow)
     # ---- chain step (what the reference's main loop does per older snapshot, src/main.cpp:154-308): metro_shift
     # (catalogue 1 -> 0 on the device, token tuples appended), upload of ONE new catalogue, match, fetch.  The two
     # synthetic catalogues alternate as "the next earlier snapshot", so every step joins the same number of IDs.
@@ -575,11 +609,14 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
         c_ms, c_dev, c_res, c_h2d = [], [], [], 0
         for k in range(n_chain + 1):                         # first one warms the allocations of the shift
             slot_src = k % 2                                 # catalogue that becomes the new slot 1 (0 = A, 1 = B)
-            c, pid, off = cats[slot_src]
+            c, pid, off, p32, base = cats[slot_src]
             t0c = time.perf_counter()
             eng.shift_halos_parts(prm)
-            hc = mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, pid.numpy().view(np.uint64), None, None)
-            eng.upload(1, prm, hc, halo_offset=off.numpy())
+            hc = mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, None if narrow else pid.numpy().view(np.uint64), None, None)
+            if narrow:
+                eng.upload(1, prm, hc, halo_offset=off.numpy(), pid32=p32.numpy().view(np.uint32), pid_base=base)
+            else:
+                eng.upload(1, prm, hc, halo_offset=off.numpy())
             info_c = eng.match_pair(prm)
             eng.fetch_result(info_c, raw=False)
             torch.cuda.synchronize(dev)
@@ -587,7 +624,7 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
                 c_ms.append((time.perf_counter() - t0c) * 1e3)
                 tt = eng.timings()
                 c_dev.append(tt["total"]); c_res.append((tt["path"], tt["resident"], [round(x, 2) for x in tt["sort_pass_ms"][:4]], round(tt["select"], 2)))
-                c_h2d = pid.numel() * 8 + off.numel() * 8
+                c_h2d = (p32.numel() * 4 if narrow else pid.numel() * 8) + off.numel() * 8
         ids_step = sum(info_c["n_tuples"])
         chain = {"value": ids_step / (statistics.median(c_ms) * 1e-3), "unit": UNIT, "ms_per_step": statistics.median(c_ms),
                  "ms_all_steps": [round(x, 1) for x in c_ms], "device_match_ms": statistics.median(c_dev),
@@ -599,8 +636,12 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
         chain = {"failed": str(ex)}
     return {"value": ids_glob / (ms / steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": ms / steps, "steps": steps, "n_trees": info["n_trees"], "chain_step": chain,
-            "path": "metro_catalogue_upload_csr x2 (pinned host: u64 particle IDs grouped by halo + i64 offsets) -> "
-                    "metro_match_pair -> metro_result_fetch (clean trees)"}
+            "h2d_gbs": h2d / (ms / steps * 1e-3) / 1e9, "ids_over_the_bus": "u32 offsets from the smallest ID" if narrow else "u64",
+            "u64_ids": wide,
+            "path": ("metro_catalogue_upload_csr32 x2 (pinned host: particle IDs grouped by halo as u32 offsets + i64 halo offsets; chunked copy, "
+                     "widened and range-checked on the device under the copy)" if narrow else
+                     "metro_catalogue_upload_csr x2 (pinned host: u64 particle IDs grouped by halo + i64 offsets)") +
+                    " -> metro_match_pair -> metro_result_fetch (clean trees)"}
 
 
 def main():

@@ -110,6 +110,8 @@ typedef struct {
 	int32_t path;                   /* 0 = LSD radix sort + run-length join, 1 = partition join, 2 = wide-key sort (IDs too wide for the packed key) */
 	int32_t resident;               /* partition join: 1 = the key buckets of catalogue 0 were still resident from the previous pair
 	                                 * of the chain (only catalogue 1 and the token tuples were partitioned) */
+	float exchange_sendrecv;        /* multi-GPU: the grouped ncclSend/ncclRecv all-to-all alone (payload over NVLink; includes waiting
+	                                 * for the slowest peer to arrive); `exchange` also covers routing counts and the scatter */
 } metro_timings;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -133,6 +135,12 @@ int metro_catalogue_upload(metro_ctx *ctx, int slot, const metro_params *prm, co
  * cat->halo is ignored (may be NULL) and the per-tuple halo index is rebuilt on the device: 8 instead of
  * 12 bytes per tuple cross the bus. */
 int metro_catalogue_upload_csr(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat, const int64_t *halo_offset);
+/* Same as metro_catalogue_upload_csr with the particle IDs as 32-bit offsets from pid_base (ID of tuple i = pid_base + pid32[i]):
+ * the form a reader can hold them in whenever the IDs it reads span less than 2^32 (a box of up to 1600^3 particles, or the
+ * particle-ID range of one rank of a larger one): 4 instead of 8 bytes per tuple cross the bus; the IDs are widened to 64 bits on
+ * the device, chunk by chunk, under the copy.  cat->pid and cat->halo are ignored (may be NULL). */
+int metro_catalogue_upload_csr32(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat, const uint32_t *pid32,
+				 uint64_t pid_base, const int64_t *halo_offset);
 /* Same, but the tuple arrays are already DEVICE pointers (zero copy; the context borrows them
  * until the next upload/shift of that slot).  Halo arrays stay host pointers. */
 int metro_catalogue_adopt_device(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat);

@@ -45,7 +45,7 @@ class ResultArrays(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("total", C.c_float), ("pack_hist", C.c_float), ("sort", C.c_float), ("join", C.c_float),
                 ("select", C.c_float), ("exchange", C.c_float), ("sort_launches", C.c_int32), ("total_launches", C.c_int32),
-                ("sort_pass_ms", C.c_float * 8), ("path", C.c_int32), ("resident", C.c_int32)]
+                ("sort_pass_ms", C.c_float * 8), ("path", C.c_int32), ("resident", C.c_int32), ("exchange_sendrecv", C.c_float)]
 
 
 class SynthSpec(C.Structure):
@@ -63,6 +63,7 @@ SYMBOLS = {
     "metro_ctx_set_stream": (C.c_int, [_P, _P]),
     "metro_catalogue_upload": (C.c_int, [_P, C.c_int, C.POINTER(Params), C.POINTER(Catalogue)]),
     "metro_catalogue_upload_csr": (C.c_int, [_P, C.c_int, C.POINTER(Params), C.POINTER(Catalogue), _P]),
+    "metro_catalogue_upload_csr32": (C.c_int, [_P, C.c_int, C.POINTER(Params), C.POINTER(Catalogue), _P, C.c_uint64, _P]),
     "metro_catalogue_adopt_device": (C.c_int, [_P, C.c_int, C.POINTER(Params), C.POINTER(Catalogue)]),
     "metro_match_pair": (C.c_int, [_P, C.POINTER(Params), C.POINTER(ResultInfo)]),
     "metro_result_fetch": (C.c_int, [_P, C.POINTER(ResultArrays)]),

@@ -29,6 +29,19 @@ int dev_reserve(metro_ctx *ctx, DevBuf &b, size_t bytes)
 	return METRO_OK;
 }
 
+// grow a buffer whose first `keep` bytes must survive (new allocation + device copy + free, only when it is too small)
+int dev_reserve_keep(metro_ctx *ctx, DevBuf &b, size_t bytes, size_t keep)
+{
+	if (bytes <= b.cap && b.p) return METRO_OK;
+	DevBuf n;
+	int rc = dev_reserve(ctx, n, bytes + bytes / 8);
+	if (rc) return rc;
+	if (b.p && keep) CUDA_TRY(ctx, cudaMemcpyAsync(n.p, b.p, keep, cudaMemcpyDeviceToDevice, ctx->stream));
+	if (b.p) { CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(b.p); }
+	b = n;
+	return METRO_OK;
+}
+
 void dev_free(DevBuf &b)
 {
 	if (b.p) cudaFree(b.p);
@@ -65,6 +78,8 @@ int metro_ctx_create(int device, metro_ctx **out)
 	memset(&ctx->res.info, 0, sizeof ctx->res.info);
 	bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
 	ctx->stream = ctx->own_stream;
+	ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+	for (int i = 0; ok && i < 5; i++) ok = cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming) == cudaSuccess;
 	for (int i = 0; ok && i < 16; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
 	for (int i = 0; ok && i < SORT_MAX_PASSES + 1; i++) ok = cudaEventCreate(&ctx->ev_pass[i]) == cudaSuccess;
 	ok = ok && cudaMallocHost(&ctx->h_counters, 64 * sizeof(u64)) == cudaSuccess;
@@ -89,7 +104,7 @@ int metro_ctx_set_stream(metro_ctx *ctx, void *cuda_stream)
 
 static void free_catalogue(DevCatalogue &c)
 {
-	DevBuf *b[] = {&c.halo_id, &c.npart, &c.npart_tot, &c.n_orphan_steps, &c.is_token, &c.pid, &c.halo, &c.type};
+	DevBuf *b[] = {&c.halo_id, &c.npart, &c.npart_tot, &c.n_orphan_steps, &c.is_token, &c.pid, &c.halo, &c.type, &c.id_rank};
 	for (DevBuf *x : b) dev_free(*x);
 	c = DevCatalogue();
 }
@@ -111,6 +126,8 @@ void metro_ctx_destroy(metro_ctx *ctx)
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
 	for (int i = 0; i < SORT_MAX_PASSES + 1; i++) cudaEventDestroy(ctx->ev_pass[i]);
+	for (int i = 0; i < 5; i++) if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
+	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -134,11 +151,12 @@ static int upload_halos(metro_ctx *ctx, DevCatalogue &c, const metro_params *prm
 	const int T = prm->nptypes;
 	cudaStream_t st = ctx->stream;
 	int rc;
-	if ((rc = dev_reserve(ctx, c.halo_id, (size_t) H * 8 + 8))) return rc;
-	if ((rc = dev_reserve(ctx, c.npart, (size_t) H * T * 4 + 8))) return rc;
-	if ((rc = dev_reserve(ctx, c.npart_tot, (size_t) H * 4 + 8))) return rc;
-	if ((rc = dev_reserve(ctx, c.n_orphan_steps, (size_t) H * 4 + 8))) return rc;
-	if ((rc = dev_reserve(ctx, c.is_token, (size_t) H + 8))) return rc;
+	const size_t Hcap = (size_t) H + (size_t) H / 16 + 4096;     // head room for the token halos a shift appends
+	if ((rc = dev_reserve(ctx, c.halo_id, Hcap * 8 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.npart, Hcap * T * 4 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.npart_tot, Hcap * 4 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.n_orphan_steps, Hcap * 4 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.is_token, Hcap + 8))) return rc;
 	if (H > 0) {
 		// Halo::nAllPart (src/Halo.cpp:63-70): plain int sum over the types
 		i32 *tot = (i32 *) malloc((size_t) H * 4);
@@ -203,7 +221,43 @@ __global__ void __launch_bounds__(256) expand_halo_kernel(const i64 *__restrict_
 	}
 }
 
-static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat, const int64_t *halo_offset)
+// One chunk of an upload, already on the device: widen 32-bit ID offsets to the u64 IDs the catalogue holds (src32 != NULL), fold
+// min / max ID and the range checks of halo index and type into the same read.  out: [0] = max pid, [1] = #invalid, [2] = min pid.
+__global__ void __launch_bounds__(256) upload_chunk_kernel(const u32 *__restrict__ src32, u64 pid_base, u64 *__restrict__ pid, const u32 *__restrict__ halo,
+							    const u8 *__restrict__ type, u64 n, u32 n_halos, u32 nptypes, u64 *out)
+{
+	u64 mx = 0, mn = ~0ull;
+	u32 bad = 0;
+	for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
+		u64 p;
+		if (src32) { p = pid_base + (u64) src32[i]; pid[i] = p; }
+		else p = pid[i];
+		mx = p > mx ? p : mx;
+		mn = p < mn ? p : mn;
+		if (halo && halo[i] >= n_halos) bad++;
+		if (type && type[i] >= nptypes) bad++;
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) {
+		const u64 o = __shfl_xor_sync(0xffffffffu, mx, off);
+		mx = o > mx ? o : mx;
+		const u64 o2 = __shfl_xor_sync(0xffffffffu, mn, off);
+		mn = o2 < mn ? o2 : mn;
+		bad += __shfl_xor_sync(0xffffffffu, bad, off);
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicMax((unsigned long long *) &out[0], (unsigned long long) mx);
+		atomicMin((unsigned long long *) &out[2], (unsigned long long) mn);
+		if (bad) atomicAdd((unsigned long long *) &out[1], (unsigned long long) bad);
+	}
+}
+
+#define UP_CHUNK (16ll << 20)   // tuples per upload chunk (128 MB of u64 IDs: 2-3 ms over PCIe 5)
+
+// Tuples host -> HBM.  The copy runs in chunks on the context's copy stream; every chunk is checked (and, for 32-bit ID offsets,
+// widened) on the compute stream while the next one is crossing the bus, so the upload costs the bus time and nothing else.
+static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat, const int64_t *halo_offset,
+			 const uint32_t *pid32 = nullptr, u64 pid_base = 0)
 {
 	int rc;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -211,11 +265,16 @@ static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, cons
 	c.valid = false; c.b_pid = nullptr; c.b_halo = nullptr; c.b_type = nullptr;
 	if ((rc = upload_halos(ctx, c, prm, cat))) return rc;
 	const i64 N = cat->n_tuples, H = cat->n_halos;
-	cudaStream_t st = ctx->stream;
-	if ((rc = dev_reserve(ctx, c.pid, (size_t) N * 8 + 8))) return rc;
-	if ((rc = dev_reserve(ctx, c.halo, (size_t) N * 4 + 64))) return rc;
-	if (cat->type) { if ((rc = dev_reserve(ctx, c.type, (size_t) N + 8))) return rc; }
+	cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+	// head room: after metro_shift this catalogue's buffers become catalogue 0 with the token tuples appended in place
+	const size_t Ncap = (size_t) N + (size_t) N / 16 + 65536;
+	if ((rc = dev_reserve(ctx, c.pid, Ncap * 8 + 8))) return rc;
+	if ((rc = dev_reserve(ctx, c.halo, Ncap * 4 + 64))) return rc;
+	if (cat->type) { if ((rc = dev_reserve(ctx, c.type, Ncap + 8))) return rc; }
 	else dev_free(c.type);
+	u64 *cnt = ctx->counters.as<u64>() + 16;      // [16] max pid, [17] #invalid, [18] min pid
+	CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * sizeof(u64), st));
+	CUDA_TRY(ctx, cudaMemsetAsync(cnt + 2, 0xFF, sizeof(u64), st));
 	if (N > 0) {
 		if (halo_offset) {
 			if (halo_offset[0] != 0 || halo_offset[H] != N) { metro_set_error(ctx, "halo_offset must run from 0 to n_tuples"); return METRO_ERR_INVALID; }
@@ -223,15 +282,40 @@ static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, cons
 			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->scratch[79].p, halo_offset, (size_t) (H + 1) * 8, cudaMemcpyHostToDevice, st));
 			expand_halo_kernel<<<(unsigned) div_up<i64>(N, 256 * 16), 256, 0, st>>>(ctx->scratch[79].as<i64>(), H, N, c.halo.as<u32>());
 			CUDA_TRY(ctx, cudaGetLastError());
-		} else {
-			CUDA_TRY(ctx, cudaMemcpyAsync(c.halo.p, cat->halo, (size_t) N * 4, cudaMemcpyHostToDevice, st));
 		}
-		CUDA_TRY(ctx, cudaMemcpyAsync(c.pid.p, cat->pid, (size_t) N * 8, cudaMemcpyHostToDevice, st));
-		if (cat->type) CUDA_TRY(ctx, cudaMemcpyAsync(c.type.p, cat->type, (size_t) N, cudaMemcpyHostToDevice, st));
+		if (pid32 && (rc = dev_reserve(ctx, ctx->scratch[78], (size_t) 2 * UP_CHUNK * 4))) return rc;
+		// the copy stream starts after everything queued on the compute stream so far (the buffers may still be in use)
+		CUDA_TRY(ctx, cudaEventRecord(ctx->ev_up[0], st));
+		CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_up[0], 0));
+		int k = 0;
+		for (i64 lo = 0; lo < N; lo += UP_CHUNK, k ^= 1) {
+			const i64 n = std::min<i64>(UP_CHUNK, N - lo);
+			u32 *stage32 = pid32 ? ctx->scratch[78].as<u32>() + (size_t) k * UP_CHUNK : nullptr;
+			if (pid32) {
+				if (lo >= 2 * UP_CHUNK) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ctx->ev_up[3 + k], 0));      // staging half consumed
+				CUDA_TRY(ctx, cudaMemcpyAsync(stage32, pid32 + lo, (size_t) n * 4, cudaMemcpyHostToDevice, cs));
+			} else CUDA_TRY(ctx, cudaMemcpyAsync(c.pid.as<u64>() + lo, cat->pid + lo, (size_t) n * 8, cudaMemcpyHostToDevice, cs));
+			if (!halo_offset) CUDA_TRY(ctx, cudaMemcpyAsync(c.halo.as<u32>() + lo, cat->halo + lo, (size_t) n * 4, cudaMemcpyHostToDevice, cs));
+			if (cat->type) CUDA_TRY(ctx, cudaMemcpyAsync(c.type.as<u8>() + lo, cat->type + lo, (size_t) n, cudaMemcpyHostToDevice, cs));
+			CUDA_TRY(ctx, cudaEventRecord(ctx->ev_up[1 + k], cs));
+			CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_up[1 + k], 0));
+			upload_chunk_kernel<<<(unsigned) std::min<i64>(div_up<i64>(n, 256 * 4), (i64) METRO_NUM_SMS_B200 * 8), 256, 0, st>>>(
+				stage32, pid_base, c.pid.as<u64>() + lo, halo_offset ? nullptr : c.halo.as<u32>() + lo, cat->type ? c.type.as<u8>() + lo : nullptr,
+				(u64) n, (u32) H, (u32) prm->nptypes, cnt);
+			CUDA_TRY(ctx, cudaGetLastError());
+			if (pid32) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_up[3 + k], st));
+		}
 	}
 	c.n_tuples = N;
 	c.gen = ctx->next_gen++;
-	if ((rc = catalogue_scan_tuples(ctx, c, prm->nptypes))) return rc;
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 16, cnt, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	c.max_pid = ctx->h_counters[16];
+	c.min_pid = N > 0 ? ctx->h_counters[18] : 0;
+	if (ctx->h_counters[17] != 0) {
+		metro_set_error(ctx, "catalogue has %llu tuples with a halo index >= n_halos or a type >= nptypes", (unsigned long long) ctx->h_counters[17]);
+		return METRO_ERR_INVALID;
+	}
 	c.valid = true;
 	ctx->nptypes = prm->nptypes;
 	ctx->res.valid = false;
@@ -247,6 +331,21 @@ int metro_catalogue_upload_csr(metro_ctx *ctx, int slot, const metro_params *prm
 	for (i64 h = 0; h < cat->n_halos; h++)
 		if (halo_offset[h + 1] < halo_offset[h]) { metro_set_error(ctx, "halo_offset decreases at halo %lld", (long long) h); return METRO_ERR_INVALID; }
 	return upload_tuples(ctx, slot, prm, cat, halo_offset);
+}
+
+int metro_catalogue_upload_csr32(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat, const uint32_t *pid32, uint64_t pid_base,
+				 const int64_t *halo_offset)
+{
+	if (!ctx) return METRO_ERR_INVALID;
+	metro_catalogue tmp;
+	if (cat) { tmp = *cat; tmp.pid = reinterpret_cast<const uint64_t *>(pid32); }          // (only tested for NULL by the checks)
+	int rc = check_catalogue(ctx, slot, prm, cat ? &tmp : nullptr, true);
+	if (rc) return rc;
+	if (!halo_offset) { metro_set_error(ctx, "halo_offset is NULL"); return METRO_ERR_INVALID; }
+	if (pid_base > ~0ull - 0xFFFFFFFFull) { metro_set_error(ctx, "pid_base + 2^32 overflows"); return METRO_ERR_INVALID; }
+	for (i64 h = 0; h < cat->n_halos; h++)
+		if (halo_offset[h + 1] < halo_offset[h]) { metro_set_error(ctx, "halo_offset decreases at halo %lld", (long long) h); return METRO_ERR_INVALID; }
+	return upload_tuples(ctx, slot, prm, cat, halo_offset, pid32, pid_base);
 }
 
 int metro_catalogue_upload(metro_ctx *ctx, int slot, const metro_params *prm, const metro_catalogue *cat)
@@ -403,6 +502,7 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	const u64 *rak, *rbk; const u32 *rac, *rbc;
 	i64 RA = 0, RB = 0, a_lo = 0, a_hi = 0;
 	ctx->exchange_bytes = 0;
+	ctx->exchange_timed = false;
 	if ((rc = comm_exchange_records(ctx, halo_bits, type_bits, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), R, &rak, &rac, &RA, &rbk,
 					&rbc, &RB))) return rc;
 	comm_owned_range(ctx, c0.n_halos, &a_lo, &a_hi);
@@ -429,6 +529,7 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	cudaEventElapsedTime(&tm.join, ctx->ev[2], ctx->ev[3]);
 	cudaEventElapsedTime(&tm.exchange, ctx->ev[3], ctx->ev[7]);
 	cudaEventElapsedTime(&tm.select, ctx->ev[7], ctx->ev[4]);
+	if (ctx->exchange_timed) cudaEventElapsedTime(&tm.exchange_sendrecv, ctx->ev[11], ctx->ev[12]);
 	if (tm.path == 1) {
 		tm.sort_pass_ms[0] = tm.pack_hist; tm.sort_pass_ms[1] = tm.sort;
 		cudaEventElapsedTime(&tm.sort_pass_ms[2], ctx->ev[2], ctx->ev[10]);

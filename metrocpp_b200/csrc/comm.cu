@@ -179,6 +179,7 @@ int comm_exchange_records(metro_ctx *ctx, int halo_bits, int type_bits, const u6
 	u64 *sk = ctx->xsend_key.as<u64>(); u32 *sc = ctx->xsend_cnt.as<u32>();
 	u64 *rak = ctx->xrecvA_key.as<u64>(); u32 *rac = ctx->xrecvA_cnt.as<u32>();
 	u64 *rbk = ctx->xrecvB_key.as<u64>(); u32 *rbc = ctx->xrecvB_cnt.as<u32>();
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[11], st));                    // the payload all-to-all alone: ev[11] .. ev[12]
 	NCCL_TRY(ctx, ncclGroupStart());
 	for (int p = 0; p < W; p++) {
 		const u64 sa = matrix[(size_t) me * 2 * W + p], sb = matrix[(size_t) me * 2 * W + W + p];
@@ -189,6 +190,8 @@ int comm_exchange_records(metro_ctx *ctx, int halo_bits, int type_bits, const u6
 		if (rb) { NCCL_TRY(ctx, ncclRecv(rbk + roffB[p], rb, ncclUint64, p, comm_of(ctx), st)); NCCL_TRY(ctx, ncclRecv(rbc + roffB[p], rb, ncclUint32, p, comm_of(ctx), st)); }
 	}
 	NCCL_TRY(ctx, ncclGroupEnd());
+	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[12], st));
+	ctx->exchange_timed = true;
 	if (dbg) {
 		const double t4 = now();
 		fprintf(stderr, "[metro] rank %d exchange: R %lld count %.2f ms, all-gather+sync %.2f ms, reserve+scatter %.2f ms, send/recv %.2f ms (nA %llu nB %llu)\n", me,

@@ -29,6 +29,9 @@ struct DevCatalogue {
 	DevBuf pid;            // u64[N]
 	DevBuf halo;           // u32[N]
 	DevBuf type;           // u8[N]
+	DevBuf id_rank;        // u32[H] rank of every halo in ascending-ID order (select.cu, cached while id_rank_gen == gen)
+	u64 id_rank_gen = 0;
+	i64 id_rank_n = -1;
 	// borrowed tuple arrays (metro_catalogue_adopt_device); override pid/halo/type when set
 	const u64 *b_pid = nullptr;
 	const u32 *b_halo = nullptr;
@@ -79,6 +82,8 @@ struct metro_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;       // stream in use
 	cudaStream_t own_stream = nullptr;   // the context's private stream
+	cudaStream_t copy_stream = nullptr;  // host -> device copies of an upload (overlapped with the per-chunk checks on `stream`)
+	cudaEvent_t ev_up[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	char err[1024] = {0};
 	int nptypes = 0;
 	DevCatalogue cat[2];
@@ -105,10 +110,12 @@ struct metro_ctx {
 	void *comm = nullptr;
 	u64 pid_base = 0;               // subtracted from every pid when the join key is packed
 	i64 exchange_bytes = 0;         // bytes this rank sent to peers in the last all-to-all
+	bool exchange_timed = false;    // ev[11] .. ev[12] bracket the grouped send/recv of the last match
 	DevBuf xsend_key, xsend_cnt, xrecvA_key, xrecvA_cnt, xrecvB_key, xrecvB_cnt, xcounts;
 };
 
 int dev_reserve(metro_ctx *ctx, DevBuf &b, size_t bytes);
+int dev_reserve_keep(metro_ctx *ctx, DevBuf &b, size_t bytes, size_t keep);
 void dev_free(DevBuf &b);
 
 // ---- device primitives (scan.cu) ---------------------------------------------------------------

@@ -555,12 +555,16 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, u32
 // load instructions, address arithmetic or register staging on the build side, and the copies fly while the table is cleared.
 #define BD_NODES 1024           // chain nodes per bucket
 #define BD_FLAG 0x80000000u     // slot / next holds a node index, not a payload
-#define BD_KPT BJ_KPT           // catalogue-0 keys per thread (all held in registers): cap2 <= BJ_THREADS * BD_KPT
-#define BD_CHUNK 2048           // keys per bulk copy == keys one build sweep of the CTA consumes (4 per thread)
-#define BD_MAXCHUNK 3           // BJ_SH / BD_CHUNK
+#ifndef BD_THREADS
+#define BD_THREADS 512
+#endif
+#define BD_MAXKEYS (BJ_THREADS * BJ_KPT)                        // largest bucket (keys per catalogue) the plan produces
+#define BD_KPT ((BD_MAXKEYS + BD_THREADS - 1) / BD_THREADS)     // catalogue-0 keys per thread (all held in registers)
+#define BD_CHUNK (4 * BD_THREADS)                               // keys per bulk copy == keys one build sweep of the CTA consumes (4 per thread)
+#define BD_MAXCHUNK ((BD_MAXKEYS + BD_CHUNK - 1) / BD_CHUNK)
 #define BD_MAX_RB 14            // 64 KB table (one CTA per SM); 13 bits and less: two CTAs per SM
 static size_t bd_table_bytes(int rb) { return ((size_t) 4 << rb) + (size_t) BD_NODES * 8; }
-static size_t bd_smem_bytes(int rb) { return bd_table_bytes(rb) + (size_t) BJ_SH * 8 + (size_t) HIT_MAX_PARTS * 16; }
+static size_t bd_smem_bytes(int rb) { return bd_table_bytes(rb) + (size_t) BJ_SH * 8 + (size_t) HIT_MAX_PARTS * 12; }
 
 __device__ __forceinline__ void bd_insert(u32 *tab, uint2 *nodes, u32 *s_nnodes, u32 r, u32 p, u32 old, u32 &ovf)
 {
@@ -571,7 +575,7 @@ __device__ __forceinline__ void bd_insert(u32 *tab, uint2 *nodes, u32 *s_nnodes,
 	}
 }
 
-__global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_direct_kernel(const u64 *__restrict__ keys0, const u64 *__restrict__ keys1,
+__global__ void __launch_bounds__(BD_THREADS, 2) bucket_join_direct_kernel(const u64 *__restrict__ keys0, const u64 *__restrict__ keys1,
 									   const u32 *__restrict__ gcount0, const u32 *__restrict__ gcount1, u64 cap2,
 									   KeyLayout L, int rb, HitPlan hp, const u64 *__restrict__ hit_base,
 									   const u32 *__restrict__ hit_cap, u32 *hit_cnt, u64 *__restrict__ hits_out,
@@ -582,11 +586,11 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_direct_kernel(const
 	u32 *tab = reinterpret_cast<u32 *>(dsm);                             // [2^rb] direct-address slots
 	uint2 *nodes = reinterpret_cast<uint2 *>(tab + (1u << rb));          // [BD_NODES] (payload, next)
 	u64 *sorted = reinterpret_cast<u64 *>(nodes + BD_NODES);             // [BJ_SH] build: catalogue-1 keys (TMA destination); sweep 2: hits sorted by partition
-	i64 *s_dst = reinterpret_cast<i64 *>(sorted + BJ_SH);                // [HIT_MAX_PARTS] global slot of a partition's run minus its local start
-	u32 *s_cnt = reinterpret_cast<u32 *>(s_dst + HIT_MAX_PARTS);        // [HIT_MAX_PARTS] hits per partition
+	u32 *s_dst = reinterpret_cast<u32 *>(sorted + BJ_SH);                // [HIT_MAX_PARTS] global slot of a partition's run minus its local start (mod 2^32; the hit buffer holds < 2^32 records)
+	u32 *s_cnt = s_dst + HIT_MAX_PARTS;                                  // [HIT_MAX_PARTS] hits per partition
 	u32 *s_start = s_cnt + HIT_MAX_PARTS;                                // [HIT_MAX_PARTS] local start of a partition in the sorted buffer
 	__shared__ __align__(8) u64 s_bar[BD_MAXCHUNK];
-	__shared__ u32 s_nnodes, s_warpsum[BJ_THREADS / 32];
+	__shared__ u32 s_nnodes, s_warpsum[BD_THREADS / 32];
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const u64 g = blockIdx.x;
 	const u32 n0 = gcount0[g], n1 = gcount1[g];
@@ -613,13 +617,13 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_direct_kernel(const
 	u64 k[BD_KPT];
 #pragma unroll
 	for (int i = 0; i < BD_KPT; i++) {
-		const u32 j = i * BJ_THREADS + tid;
+		const u32 j = i * BD_THREADS + tid;
 		k[i] = j < n0 ? ld_stream_u64(src0 + j) : 0ull;
 	}
 	{
 		uint4 *t4 = reinterpret_cast<uint4 *>(tab);
-		for (u32 i = tid; i < (1u << rb) / 4; i += BJ_THREADS) t4[i] = make_uint4(0u, 0u, 0u, 0u);
-		for (u32 i = tid; i < HIT_MAX_PARTS; i += BJ_THREADS) s_cnt[i] = 0;
+		for (u32 i = tid; i < (1u << rb) / 4; i += BD_THREADS) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+		for (u32 i = tid; i < HIT_MAX_PARTS; i += BD_THREADS) s_cnt[i] = 0;
 	}
 	u32 ovf = 0;                // overflow causes: 2 table (chain nodes) full, 4 more hits than the sorted buffer holds, 8 hit region full
 	__syncthreads();
@@ -649,23 +653,29 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_direct_kernel(const
 	const u32 tmask = L.type_mask;
 	const int dsh = tb + hp.log_hp;                                       // key -> hit partition of its halo
 	const u32 dmask = L.halo_mask >> hp.log_hp;
-	// sweep 1: hits per key (its chain length) -> counter of the key's partition; the value returned is the key's rank there
-	u32 rank[BD_KPT];
+	// sweep 1: hits per key (its chain length) -> counter of the key's partition; the value returned is the key's rank there.
+	// From here on a key is its slot value v and its low word kl = (snap, halo, type): the pid has done its job.
+	u32 rank[BD_KPT], v[BD_KPT], kl[BD_KPT];
 #pragma unroll
 	for (int i = 0; i < BD_KPT; i++) {
-		const u32 v = tab[(u32) (k[i] >> psft) & rmask];                  // (a key past the end is 0: slot 0 is read and ignored)
-		u32 len = v != 0u ? 1u : 0u;
-		if (v & BD_FLAG) {
-			u32 nx = nodes[v & ~BD_FLAG].y;
+		const u32 t = tab[(u32) (k[i] >> psft) & rmask];                  // (a key past the end is 0: slot 0 is read and ignored)
+		v[i] = i * BD_THREADS + tid < n0 ? t : 0u;
+		kl[i] = (u32) k[i];
+	}
+#pragma unroll
+	for (int i = 0; i < BD_KPT; i++) {
+		u32 len = v[i] != 0u ? 1u : 0u;
+		if (v[i] & BD_FLAG) {
+			u32 nx = nodes[v[i] & ~BD_FLAG].y;
 			len = 2u;
 			while (nx & BD_FLAG) { nx = nodes[nx & ~BD_FLAG].y; len++; }
 		}
 		rank[i] = 0;
-		if (i * BJ_THREADS + tid < n0 && len) rank[i] = atomicAdd(&s_cnt[((u32) k[i] >> dsh) & dmask], len);
+		if (len) rank[i] = atomicAdd(&s_cnt[(kl[i] >> dsh) & dmask], len);
 	}
 	__syncthreads();
 	// exclusive scan of the partition counts (2 per thread); region space reserved with one global atomic per partition
-	constexpr int BPT = HIT_MAX_PARTS / BJ_THREADS;
+	constexpr int BPT = (HIT_MAX_PARTS + BD_THREADS - 1) / BD_THREADS;
 	u32 loc[BPT], sum = 0;
 #pragma unroll
 	for (int q = 0; q < BPT; q++) { const u32 b = tid * BPT + q; loc[q] = b < hp.nbh ? s_cnt[b] : 0u; sum += loc[q]; }
@@ -679,23 +689,20 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_direct_kernel(const
 	__syncthreads();
 	u32 pre = 0, nh = 0;
 #pragma unroll
-	for (int w = 0; w < BJ_THREADS / 32; w++) { const u32 x = s_warpsum[w]; pre += (w < warp) ? x : 0u; nh += x; }
+	for (int w = 0; w < BD_THREADS / 32; w++) { const u32 x = s_warpsum[w]; pre += (w < warp) ? x : 0u; nh += x; }
 	if (nh > hcap) {                                                     // more hits than the buffer holds (same decision in every thread)
 		if (tid == 0) atomicOr(overflow, 4u | ovf);
 		return;
 	}
 	u32 run = pre + incl - sum;
+	// the global reservations are issued here and consumed after sweep 2, which hides their latency (an L2 round trip under contention)
+	u32 g0[BPT], run0[BPT];
 #pragma unroll
 	for (int q = 0; q < BPT; q++) {
 		const u32 b = tid * BPT + q;
+		g0[q] = 0; run0[q] = run;
 		if (b < hp.nbh) {
-			i64 dst = INT64_MIN;
-			if (loc[q]) {
-				const u32 g0 = atomicAdd(&hit_cnt[b * CSTRIDE], loc[q]);
-				if ((u64) g0 + loc[q] <= (u64) hit_cap[b]) dst = (i64) (hit_base[b] + g0) - (i64) run;
-				else ovf |= 8u;
-			}
-			s_dst[b] = dst;
+			if (loc[q]) g0[q] = atomicAdd(&hit_cnt[b * CSTRIDE], loc[q]);
 			s_start[b] = run;
 			run += loc[q];
 		}
@@ -705,27 +712,37 @@ __global__ void __launch_bounds__(BJ_THREADS, 2) bucket_join_direct_kernel(const
 	// sweep 2: every member of the slot's chain is one hit, written at its final place in the partition-sorted buffer
 #pragma unroll
 	for (int i = 0; i < BD_KPT; i++) {
-		u32 v = i * BJ_THREADS + tid < n0 ? tab[(u32) (k[i] >> psft) & rmask] : 0u;
-		if (v) {
-			const u32 kl = (u32) k[i];
-			const u64 recA = ((u64) ((u32) (k[i] >> tb) & L.halo_mask) << hp.rec_a_shift) | (u64) ((kl & tmask) << tb);
-			u32 pos = s_start[(kl >> dsh) & dmask] + rank[i];
+		u32 w = v[i];
+		if (w) {
+			const u64 recA = ((u64) ((kl[i] >> tb) & L.halo_mask) << hp.rec_a_shift) | (u64) ((kl[i] & tmask) << tb);
+			u32 pos = s_start[(kl[i] >> dsh) & dmask] + rank[i];
 			do {
 				u32 p;
-				if (v & BD_FLAG) { const uint2 nd = nodes[v & ~BD_FLAG]; p = nd.x; v = nd.y; }
-				else { p = v; v = 0u; }
+				if (w & BD_FLAG) { const uint2 nd = nodes[w & ~BD_FLAG]; p = nd.x; w = nd.y; }
+				else { p = w; w = 0u; }
 				const u32 pm = p - 1u;
 				sorted[pos++] = recA | (u64) (((pm >> tb) << (2 * tb)) | (pm & tmask));
-			} while (v);
+			} while (w);
 		}
 	}
-	__syncthreads();
+#pragma unroll
+	for (int q = 0; q < BPT; q++) {
+		const u32 b = tid * BPT + q;
+		if (b < hp.nbh && loc[q]) {
+			// a partition whose region is full keeps a valid destination only in the flag: the whole attempt is discarded by the caller
+			if ((u64) g0[q] + loc[q] <= (u64) hit_cap[b]) s_dst[b] = (u32) (hit_base[b] + g0[q]) - run0[q];
+			else { s_dst[b] = 0xFFFFFFFFu; ovf |= 8u; }
+		}
+	}
+	if (__syncthreads_or(ovf & 8u)) {                                    // (block-uniform) nothing is written once a region overflowed
+		if (ovf) atomicOr(overflow, ovf);
+		return;
+	}
 	const int psh = hp.rec_a_shift + hp.log_hp;
 #pragma unroll 4
-	for (u32 j = tid; j < nh; j += BJ_THREADS) {
+	for (u32 j = tid; j < nh; j += BD_THREADS) {
 		const u64 r = sorted[j];
-		const i64 dst = s_dst[(u32) (r >> psh)];
-		if (dst != INT64_MIN) st_stream_u64(hits_out + dst + (i64) j, r);
+		st_stream_u64(hits_out + (u32) (s_dst[(u32) (r >> psh)] + j), r);
 	}
 	if (ovf) atomicOr(overflow, ovf);
 }
@@ -985,8 +1002,11 @@ static HitPlan make_hit_plan(int rec_halo_bits, int type_bits, i64 H0)
 {
 	HitPlan hp;
 	hp.rec_a_shift = rec_halo_bits + 2 * type_bits;
-	hp.ways = 4; hp.log_hs = 11;                                    // 2048 halos x 4 ways x 8 B = 64 KB: two pass-D blocks per SM
-	hp.log_hp = 11;
+	// 2048 halos x 4 ways x 8 B = 64 KB: two pass-D blocks per SM (METRO_LOG_HP=12: 4096 halos per range from the start, one
+	// 1024-thread block per SM - half as many ranges for pass C to partition the hits into)
+	static const int base_log = getenv("METRO_LOG_HP") && atoi(getenv("METRO_LOG_HP")) == 12 ? 12 : 11;
+	hp.ways = 4; hp.log_hs = base_log;
+	hp.log_hp = base_log;
 	auto parts = [&](int lg) { return (u64) div_up<i64>(std::max<i64>(H0, 1), 1ll << lg); };
 	while (parts(hp.log_hp) > HIT_MAX_PARTS && hp.log_hp < 11 + HR_MAX_SUB_LOG) hp.log_hp++;
 	if (hp.log_hp > hp.log_hs) hp.log_hs = 12;                       // sub-range mode: 4096 halos x 4 ways = 128 KB, one 1024-thread block per SM
@@ -1109,7 +1129,7 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 		const u32 wcap = (test_wcap && !finer_plan) ? std::min<u32>(test_wcap, BJ_WCAP) : (u32) BJ_WCAP;
 		const int rb = L.pid_bits - P.b1 - P.b2;
 		const u64 *kb = ctx->keys_b.as<u64>();
-		if (!no_direct && rb <= BD_MAX_RB && L.snap_shift <= 30) {
+		if (!no_direct && rb <= BD_MAX_RB && L.snap_shift <= 30 && hits_cap < (1ull << 32)) {
 			// few residual pid bits (dense IDs): direct-address table
 			const int rbk = rb < 2 ? 2 : rb;
 			const size_t smem = bd_smem_bytes(rbk);
@@ -1121,9 +1141,9 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 				pf_b[h] = (u32) std::min<u64>(P.cap2 * 8, (((u64) (m + sqrt(m)) + 2) & ~1ull) * 8);
 			}
 			// test hook: a smaller hit capacity for the default bucket size forces the finer-bucket retry
-			const u32 hcap = (test_wcap && !finer_plan) ? std::min<u32>(test_wcap * (BJ_THREADS / 32), BJ_SH) : (u32) BJ_SH;
+			const u32 hcap = (test_wcap && !finer_plan) ? std::min<u32>(test_wcap * 16, BJ_SH) : (u32) BJ_SH;
 			CUDA_TRY(ctx, cudaFuncSetAttribute(bucket_join_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-			bucket_join_direct_kernel<<<(unsigned) nbk, BJ_THREADS, smem, st>>>(kb + (size_t) half0 * nbk * P.cap2, kb + (size_t) half1 * nbk * P.cap2,
+			bucket_join_direct_kernel<<<(unsigned) nbk, BD_THREADS, smem, st>>>(kb + (size_t) half0 * nbk * P.cap2, kb + (size_t) half1 * nbk * P.cap2,
 											    g2 + (size_t) half0 * nbk, g2 + (size_t) half1 * nbk, P.cap2, L, rbk, hp, hit_base,
 											    hit_cap, hit_cnt, ctx->keys_a.as<u64>(), counters, ovf, hcap, pf_dist, pf_b[half0], pf_b[half1]);
 		} else {
@@ -1141,7 +1161,8 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	hit_units_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(hit_cnt, hp.nbh, units, n_units);
 	CUDA_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
-	if (hp.log_hp == hp.log_hs) rc = launch_reduce<4, false, HR_THREADS>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
+	if (hp.log_hp == hp.log_hs && hp.log_hs == 12) rc = launch_reduce<4, false, 2 * HR_THREADS>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
+	else if (hp.log_hp == hp.log_hs) rc = launch_reduce<4, false, HR_THREADS>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
 	else rc = launch_reduce<4, true, 2 * HR_THREADS>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);
 	if (rc) return rc;
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, counters, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));

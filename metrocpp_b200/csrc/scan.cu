@@ -1,5 +1,5 @@
 // scan.cu -- exclusive prefix sum (u32) used by the selection stage for ordered compaction and
-// CSR offsets.  Reduce-then-scan over 4096-element tiles, recursing on the tile sums.
+// CSR offsets.  One pass: 4096-element tiles chained by a decoupled look-back.
 #include "context.cuh"
 
 #define SC_THREADS 256
@@ -28,35 +28,6 @@ __device__ __forceinline__ u32 block_exclusive_scan(u32 v, u32 *s_warp, u32 *blo
 	return pre + incl - v;
 }
 
-// tile-local exclusive scan; tile totals to sums[]
-__global__ void __launch_bounds__(SC_THREADS) scan_tiles_kernel(const u32 *__restrict__ in, u32 *__restrict__ out,
-								i64 n, u32 *__restrict__ sums)
-{
-	__shared__ u32 s_warp[SC_THREADS / 32];
-	const i64 base = (i64) blockIdx.x * SC_TILE + (i64) threadIdx.x * SC_ITEMS;
-	u32 v[SC_ITEMS];
-	u32 sum = 0;
-#pragma unroll
-	for (int i = 0; i < SC_ITEMS; i++) {
-		v[i] = base + i < n ? in[base + i] : 0u;
-		sum += v[i];
-	}
-	u32 tot;
-	u32 run = block_exclusive_scan(sum, s_warp, &tot);
-#pragma unroll
-	for (int i = 0; i < SC_ITEMS; i++) {
-		if (base + i < n) out[base + i] = run;
-		run += v[i];
-	}
-	if (threadIdx.x == 0) sums[blockIdx.x] = tot;
-}
-
-__global__ void scan_add_kernel(u32 *__restrict__ out, i64 n, const u32 *__restrict__ offs)
-{
-	const i64 i = (i64) blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) out[i] += offs[i / SC_TILE];
-}
-
 // single block: scan up to SC_TILE elements and write the grand total
 __global__ void __launch_bounds__(SC_THREADS) scan_top_kernel(u32 *__restrict__ data, i64 n, u64 *__restrict__ total)
 {
@@ -79,24 +50,56 @@ __global__ void __launch_bounds__(SC_THREADS) scan_top_kernel(u32 *__restrict__ 
 	if (threadIdx.x == 0 && total) *total = tot;
 }
 
-static int scan_rec(metro_ctx *ctx, cudaStream_t st, const u32 *in, u32 *out, i64 n, u32 *tmp, u64 *d_total)
+// ---- single pass: decoupled look-back over 4096-element tiles ---------------------------------
+// Tiles take a ticket (so a tile only ever waits for tiles that started before it), publish their sum, look back over the
+// predecessors' (aggregate | inclusive prefix) words and publish their own inclusive prefix.  One launch per scan instead of three.
+#define SC_AGG (1ull << 62)
+#define SC_INC (2ull << 62)
+#define SC_VAL ((1ull << 62) - 1ull)
+__global__ void __launch_bounds__(SC_THREADS) scan_lookback_kernel(const u32 *__restrict__ in, u32 *__restrict__ out, i64 n, u64 *state /* [tiles] zeroed */,
+								   u32 *ticket /* zeroed */, u64 *__restrict__ total)
 {
-	if (n <= SC_TILE) {
-		if (in != out) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, (size_t) n * 4, cudaMemcpyDeviceToDevice, st));
-		scan_top_kernel<<<1, SC_THREADS, 0, st>>>(out, n, d_total);
-		CUDA_TRY(ctx, cudaGetLastError());
-		ctx->launches++;
-		return METRO_OK;
+	__shared__ u32 s_warp[SC_THREADS / 32];
+	__shared__ u32 s_tile;
+	__shared__ u64 s_prefix;
+	if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+	__syncthreads();
+	const u32 tile = s_tile;
+	const i64 base = (i64) tile * SC_TILE + (i64) threadIdx.x * SC_ITEMS;
+	u32 v[SC_ITEMS];
+	u32 sum = 0;
+#pragma unroll
+	for (int i = 0; i < SC_ITEMS; i++) {
+		v[i] = base + i < n ? in[base + i] : 0u;
+		sum += v[i];
 	}
-	const i64 tiles = div_up<i64>(n, SC_TILE);
-	scan_tiles_kernel<<<(unsigned) tiles, SC_THREADS, 0, st>>>(in, out, n, tmp);
-	CUDA_TRY(ctx, cudaGetLastError());
-	int rc = scan_rec(ctx, st, tmp, tmp, tiles, tmp + tiles, d_total);
-	if (rc) return rc;
-	scan_add_kernel<<<(unsigned) div_up<i64>(n, 256), 256, 0, st>>>(out, n, tmp);
-	CUDA_TRY(ctx, cudaGetLastError());
-	ctx->launches += 2;
-	return METRO_OK;
+	u32 tot;
+	u32 run = block_exclusive_scan(sum, s_warp, &tot);
+	if (threadIdx.x == 0) {
+		volatile u64 *vs = state;
+		u64 prefix = 0;
+		if (tile == 0) vs[0] = SC_INC | (u64) tot;
+		else {
+			vs[tile] = SC_AGG | (u64) tot;
+			__threadfence();
+			for (i64 t = (i64) tile - 1; t >= 0; t--) {
+				u64 w;
+				do { w = vs[t]; } while ((w >> 62) == 0);
+				prefix += w & SC_VAL;
+				if ((w >> 62) == 2) break;
+			}
+			vs[tile] = SC_INC | (prefix + (u64) tot);
+		}
+		s_prefix = prefix;
+		if (total && (i64) (tile + 1) * SC_TILE >= n) *total = prefix + (u64) tot;
+	}
+	__syncthreads();
+	run += (u32) s_prefix;
+#pragma unroll
+	for (int i = 0; i < SC_ITEMS; i++) {
+		if (base + i < n) out[base + i] = run;
+		run += v[i];
+	}
 }
 
 int scan_exclusive_u32(metro_ctx *ctx, cudaStream_t st, const u32 *in, u32 *out, i64 n, u64 *d_total)
@@ -105,9 +108,20 @@ int scan_exclusive_u32(metro_ctx *ctx, cudaStream_t st, const u32 *in, u32 *out,
 		if (d_total) CUDA_TRY(ctx, cudaMemsetAsync(d_total, 0, sizeof(u64), st));
 		return METRO_OK;
 	}
-	// tile sums of every level: n/4096 + n/4096^2 + ... < n/4000 + 8
-	size_t need = ((size_t) n / 4000 + 64) * sizeof(u32);
-	int rc = dev_reserve(ctx, ctx->scan_tmp, need);
+	if (n <= SC_TILE) {
+		if (in != out) CUDA_TRY(ctx, cudaMemcpyAsync(out, in, (size_t) n * 4, cudaMemcpyDeviceToDevice, st));
+		scan_top_kernel<<<1, SC_THREADS, 0, st>>>(out, n, d_total);
+		CUDA_TRY(ctx, cudaGetLastError());
+		ctx->launches++;
+		return METRO_OK;
+	}
+	const i64 tiles = div_up<i64>(n, SC_TILE);
+	int rc = dev_reserve(ctx, ctx->scan_tmp, (size_t) tiles * 8 + 64);
 	if (rc) return rc;
-	return scan_rec(ctx, st, in, out, n, ctx->scan_tmp.as<u32>(), d_total);
+	u64 *state = ctx->scan_tmp.as<u64>();
+	CUDA_TRY(ctx, cudaMemsetAsync(state, 0, (size_t) tiles * 8 + 8, st));
+	scan_lookback_kernel<<<(unsigned) tiles, SC_THREADS, 0, st>>>(in, out, n, state, reinterpret_cast<u32 *>(state + tiles), d_total);
+	CUDA_TRY(ctx, cudaGetLastError());
+	ctx->launches++;
+	return METRO_OK;
 }

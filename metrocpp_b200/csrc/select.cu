@@ -64,15 +64,48 @@ __device__ __forceinline__ void hit_decode(const HitLayout &h, u64 hk, u32 &A, u
 	A = (u32) ((hk >> (2 * h.type_bits + h.halo_bits)) & hm);
 }
 
-// record -> sort key (A, idRank1[B]) so that equal (A,B) are adjacent and B ascends by halo ID
-__global__ void rec_key_kernel(const u64 *rec, i64 n, HitLayout hl, const u32 *rank1, u64 *key, u32 *val)
+// record -> (group halo, order key inside the group): forward (A, idRank1[B]), backward (B, idRank0[A])
+__global__ void rec_split_kernel(const u64 *rec, i64 n, HitLayout hl, const u32 *rank_other, int backward, u32 *main, u32 *sec)
 {
 	TID;
 	if (i >= n) return;
 	u32 A, B, tA, tB;
 	hit_decode(hl, rec[i], A, B, tA, tB);
-	key[i] = ((u64) A << hl.halo_bits) | rank1[B];      // 2 halo_bits wide: one radix pass per 8 bits of it
-	val[i] = (u32) i;
+	main[i] = backward ? B : A;
+	sec[i] = rank_other[backward ? A : B];
+}
+
+__global__ void rank_of_kernel(const u32 *idx, const u32 *rank, i64 n_max, const u64 *nd, u32 *out)
+{
+	TID;
+	if (i < n_max && i < (i64) *nd) out[i] = rank[idx[i]];
+}
+
+// counting sort by group: element i goes to some slot of its group's range (the order inside a group is fixed afterwards by the
+// segmented sort on the order key)
+__global__ void group_scatter_kernel(const u32 *main, const u32 *sec, i64 n_max, const u64 *nd, const u32 *segoff, u32 *cursor, u32 *slot_idx, u64 *slot_key)
+{
+	TID;
+	if (i >= n_max || (nd && i >= (i64) *nd)) return;
+	const u32 m = main[i];
+	const u32 p = segoff[m] + atomicAdd(&cursor[m], 1u);
+	slot_idx[p] = (u32) i;
+	slot_key[p] = (u64) sec[i];
+}
+
+__global__ void group_perm_kernel(const u32 *sidx, const u32 *slot_idx, const u64 *slot_key, const u32 *main, i64 n_max, const u64 *nd, u32 *perm, u64 *key_sorted)
+{
+	TID;
+	if (i >= n_max || (nd && i >= (i64) *nd)) return;
+	const u32 s = sidx[i], e = slot_idx[s];
+	perm[i] = e;
+	key_sorted[i] = ((u64) main[e] << 32) | (u64) (u32) slot_key[s];
+}
+
+__global__ void count_group_kernel(const u32 *main, i64 n_max, const u64 *nd, u32 *cnt)
+{
+	TID;
+	if (i < n_max && (!nd || i < (i64) *nd)) atomicAdd(&cnt[main[i]], 1u);
 }
 
 __global__ void head_flag_kernel(const u64 *key, i64 n, u32 *flag)
@@ -98,11 +131,13 @@ __global__ void pair_merge_kernel(const u64 *rec, const u32 *rec_cnt, const u32 
 	atomicAdd(&ptot[p], c);
 }
 
+// Element counts that only the device knows (distinct pairs, kept pairs, clean entries) are read from device memory:
+// kernels are launched over an upper bound (the record count) and stop at *nd - no host round trip in the middle of the stage.
 // AssignMap threshold: keep iff sum_t nCommon > minPartCmp (strict)
-__global__ void keep_flag_kernel(const i32 *ptot, i64 n, i32 min_part_cmp, u32 *flag)
+__global__ void keep_flag_kernel(const i32 *ptot, i64 n_max, const u64 *nd, i32 min_part_cmp, u32 *flag)
 {
 	TID;
-	if (i < n) flag[i] = ptot[i] > min_part_cmp ? 1u : 0u;
+	if (i < n_max) flag[i] = (i < (i64) *nd && ptot[i] > min_part_cmp) ? 1u : 0u;
 }
 
 __global__ void pair_compact_kernel(const u32 *flag, const u32 *scan, i64 n, int T, const u32 *pA, const u32 *pB,
@@ -115,20 +150,13 @@ __global__ void pair_compact_kernel(const u32 *flag, const u32 *scan, i64 n, int
 	for (int t = 0; t < T; t++) { kF[(i64) d * T + t] = pF[i * T + t]; kK[(i64) d * T + t] = pK[i * T + t]; }
 }
 
-__global__ void count_by_kernel(const u32 *main, i64 n, u32 *cnt) { TID; if (i < n) atomicAdd(&cnt[main[i]], 1u); }
+__global__ void count_by_kernel(const u32 *main, const u64 *nd, u32 *cnt) { TID; if (i < (i64) *nd) atomicAdd(&cnt[main[i]], 1u); }
 
-// backward ordering key: (B, idRank0[A])
-__global__ void bwd_key_kernel(const u32 *kA, const u32 *kB, const u32 *rank0, int hbits, i64 n, u64 *key, u32 *val)
-{
-	TID;
-	if (i < n) { key[i] = ((u64) kB[i] << hbits) | rank0[kA[i]]; val[i] = (u32) i; }
-}
-
-__global__ void gather_dir_kernel(const u32 *perm, i64 n, int T, const u32 *src_main, const u32 *src_other, const i32 *src_nc,
+__global__ void gather_dir_kernel(const u32 *perm, const u64 *nd, int T, const u32 *src_main, const u32 *src_other, const i32 *src_nc,
 				  const i32 *src_tot, u32 *m_main, u32 *m_other, i32 *m_nc, i32 *m_tot)
 {
 	TID;
-	if (i >= n) return;
+	if (i >= (i64) *nd) return;
 	const u32 s = perm[i];
 	m_main[i] = src_main[s]; m_other[i] = src_other[s]; m_tot[i] = src_tot[s];
 	for (int t = 0; t < T; t++) m_nc[i * T + t] = src_nc[(i64) s * T + t];
@@ -136,10 +164,10 @@ __global__ void gather_dir_kernel(const u32 *perm, i64 n, int T, const u32 *src_
 
 // merit of element i (position iM inside its segment) and the (main, ~merit) sort key
 __global__ void merit_key_kernel(const u32 *m_main, const u32 *m_other, const i32 *m_tot, const u32 *segoff, const u32 *segcnt,
-				 const i32 *np_main, const i32 *np_other, i64 n, u32 *merit, u64 *key, u32 *val)
+				 const i32 *np_main, const i32 *np_other, const u64 *nd, u32 *merit, u64 *key, u32 *val)
 {
 	TID;
-	if (i >= n) return;
+	if (i >= (i64) *nd) return;
 	const u32 a = m_main[i];
 	u32 mb = 0, low = 0;
 	if (segcnt[a] > 1) {
@@ -234,10 +262,10 @@ __global__ void __launch_bounds__(256) seg_sort_long_kernel(const u64 *__restric
 
 // SortIndexes tie quirk: inside a run of equal merits every position receives the run's first
 // element (lowest pre-sort index, which the stable sort put first).
-__global__ void tie_quirk_kernel(const u32 *sidx, const u32 *m_main, const u32 *merit, const u32 *segoff, i64 n, u32 *src)
+__global__ void tie_quirk_kernel(const u32 *sidx, const u32 *m_main, const u32 *merit, const u32 *segoff, const u64 *nd, u32 *src)
 {
 	TID;
-	if (i >= n) return;
+	if (i >= (i64) *nd) return;
 	const u32 me = sidx[i];
 	const u32 a = m_main[me];
 	const u32 v = float_sortable(merit[me]);
@@ -247,11 +275,11 @@ __global__ void tie_quirk_kernel(const u32 *sidx, const u32 *m_main, const u32 *
 	src[i] = sidx[q];
 }
 
-__global__ void emit_raw_kernel(const u32 *src, i64 n, int T, const u32 *m_main, const u32 *m_other, const i32 *m_nc, const u32 *merit,
+__global__ void emit_raw_kernel(const u32 *src, const u64 *nd, int T, const u32 *m_main, const u32 *m_other, const i32 *m_nc, const u32 *merit,
 				const u32 *segcnt, u32 *raw_main, i32 *raw_prog, i32 *raw_nc, u32 *raw_merit)
 {
 	TID;
-	if (i >= n) return;
+	if (i >= (i64) *nd) return;
 	const u32 s = src[i];
 	const u32 a = m_main[s];
 	raw_main[i] = a;
@@ -260,11 +288,11 @@ __global__ void emit_raw_kernel(const u32 *src, i64 n, int T, const u32 *m_main,
 	for (int t = 0; t < T; t++) raw_nc[i * T + t] = m_nc[(i64) s * T + t];
 }
 
-__global__ void off32_to_64_kernel(const u32 *off, i64 n, u64 total, i64 *out)
+__global__ void off32_to_64_kernel(const u32 *off, i64 n, const u64 *total, i64 *out)
 {
 	TID;
 	if (i < n) out[i] = off[i];
-	if (i == n) out[n] = (i64) total;
+	if (i == n) out[n] = (i64) *total;
 }
 
 // best descendant of every catalogue-1 halo: head of its backward tree (-1 if none)
@@ -275,10 +303,11 @@ __global__ void best_desc_kernel(const u32 *off1, const u32 *cnt1, const i32 *ra
 }
 
 // mutual-best filter (CleanTrees :539-568): keep B iff ID(bestDesc[B]) == ID(A)
-__global__ void clean_flag_kernel(const u32 *raw_main0, const i32 *raw_prog0, i64 n, const i32 *best, const u64 *id0, u32 *flag, u32 *cntc)
+__global__ void clean_flag_kernel(const u32 *raw_main0, const i32 *raw_prog0, i64 n_max, const u64 *nd, const i32 *best, const u64 *id0, u32 *flag, u32 *cntc)
 {
 	TID;
-	if (i >= n) return;
+	if (i >= n_max) return;
+	if (i >= (i64) *nd) { flag[i] = 0; return; }
 	const u32 a = raw_main0[i];
 	const i32 d = best[raw_prog0[i]];
 	const u32 f = (d >= 0 && id0[d] == id0[a]) ? 1u : 0u;
@@ -305,11 +334,11 @@ __global__ void orphan_kernel(const u32 *cntc, const i32 *nptot0, const i32 *nor
 	has_tree[i] = (cntc[i] + tk) > 0 ? 1u : 0u;
 }
 
-__global__ void clean_fill_kernel(const u32 *flag, const u32 *scan, i64 n, int T, const u32 *raw_main0, const i32 *raw_prog0,
+__global__ void clean_fill_kernel(const u32 *flag, const u32 *scan, const u64 *nd, int T, const u32 *raw_main0, const i32 *raw_prog0,
 				  const i32 *raw_nc0, const u32 *cstart, const u32 *coff, u32 *c_main, u32 *c_other, i32 *c_nc, i32 *c_tot)
 {
 	TID;
-	if (i >= n || !flag[i]) return;
+	if (i >= (i64) *nd || !flag[i]) return;
 	const u32 a = raw_main0[i];
 	const u32 d = coff[a] + (scan[i] - cstart[a]);
 	c_main[d] = a;
@@ -349,20 +378,20 @@ __global__ void token_emit_kernel(const u32 *token, const u32 *kscan, i64 H0, i3
 	if (i < H0 && token[i]) token_halo[kscan[i]] = (i32) i;
 }
 
-__global__ void set_i64_kernel(i64 *p, i64 v) { *p = v; }
+// tree_off[n_trees] = clean entries (both counts live on the device)
+__global__ void tree_off_end_kernel(i64 *tree_off, const u64 *n_trees, const u64 *n_clean) { tree_off[*n_trees] = (i64) *n_clean; }
 
 // ---- host orchestration ------------------------------------------------------------------------
+// The stage runs WITHOUT a host round trip until its very end: counts that only the device knows (distinct pairs P, kept pairs K,
+// clean entries C, trees, tokens) stay in the context's device counters; buffers are sized by upper bounds the host does know
+// (records in, halos) and kernels launched over those bounds stop at the device-side count.  One copy of the counters + one stream
+// synchronisation at the end give the caller its sizes.
 #define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
 #define RES(b, bytes) TRY(dev_reserve(ctx, (b), (size_t) (bytes) + 256))
 #define LAUNCHED() do { CUDA_TRY(ctx, cudaGetLastError()); ctx->launches++; } while (0)
 
-static int read_total(metro_ctx *ctx, const u64 *d, u64 *h)
-{
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 8, d, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-	*h = ctx->h_counters[8];
-	return METRO_OK;
-}
+// device counter slots (u64) of this stage inside metro_ctx::counters
+enum { C_UNTRACKED = 4, C_CLEAN = 5, C_TREES = 6, C_TOKENS = 7, C_IDFLAG = 20, C_LISTS = 21, C_P_FWD = 30, C_K_FWD = 31, C_P_BWD = 32, C_K_BWD = 33 };
 
 // key/value radix sort on bits [0, end_bit) using the four ping-pong buffers
 static int sort_kv(metro_ctx *ctx, u64 *ka, u64 *kb, u32 *va, u32 *vb, i64 n, int end_bit, u64 **rk, u32 **rv)
@@ -382,116 +411,139 @@ __global__ void ids_descend_kernel(const u64 *id, i64 n, u64 *flag)
 	if (i + 1 < n && id[i] > id[i + 1]) *flag = 1;
 }
 
-// argsort of the halo IDs of one catalogue: rank[h] = position of h in ascending-ID order
-static int id_ranks(metro_ctx *ctx, const DevCatalogue &c, DevBuf &rank_buf, DevBuf *tmp)
+// argsort of the halo IDs of one catalogue: rank[h] = position of h in ascending-ID order.  Cached with the catalogue
+// (DevCatalogue::id_rank, valid while id_rank_gen == gen and the halo count is unchanged): a chain pays for it once per snapshot.
+static int id_ranks(metro_ctx *ctx, DevCatalogue &c, DevBuf *tmp)
 {
 	cudaStream_t st = ctx->stream;
 	const i64 H = c.n_halos;
-	RES(rank_buf, H * 4);
+	if (c.id_rank.p && c.id_rank_gen == c.gen && c.id_rank_n == H) return METRO_OK;
+	RES(c.id_rank, H * 4);
+	c.id_rank_gen = c.gen; c.id_rank_n = H;
 	if (H == 0) return METRO_OK;
 	{	// catalogues normally list their halos by ascending ID already: the rank is the index (saves 8 radix passes)
-		u64 *flag = ctx->counters.as<u64>() + 20, descends = 0;
+		u64 *flag = ctx->counters.as<u64>() + C_IDFLAG;
 		CUDA_TRY(ctx, cudaMemsetAsync(flag, 0, sizeof(u64), st));
 		ids_descend_kernel<<<GRID(H), TPB, 0, st>>>(c.halo_id.as<u64>(), H, flag); LAUNCHED();
-		TRY(read_total(ctx, flag, &descends));
-		if (!descends) { iota_kernel<<<GRID(H), TPB, 0, st>>>(rank_buf.as<u32>(), H); LAUNCHED(); return METRO_OK; }
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 8, flag, sizeof(u64), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		if (!ctx->h_counters[8]) { iota_kernel<<<GRID(H), TPB, 0, st>>>(c.id_rank.as<u32>(), H); LAUNCHED(); return METRO_OK; }
 	}
 	RES(tmp[0], H * 8); RES(tmp[1], H * 8); RES(tmp[2], H * 4); RES(tmp[3], H * 4);
 	copy_u64_kernel<<<GRID(H), TPB, 0, st>>>(c.halo_id.as<u64>(), tmp[0].as<u64>(), H); LAUNCHED();
 	iota_kernel<<<GRID(H), TPB, 0, st>>>(tmp[2].as<u32>(), H); LAUNCHED();
 	u64 *rk; u32 *rv;
 	TRY(sort_kv(ctx, tmp[0].as<u64>(), tmp[1].as<u64>(), tmp[2].as<u32>(), tmp[3].as<u32>(), H, 64, &rk, &rv));
-	invert_perm_kernel<<<GRID(H), TPB, 0, st>>>(rv, rank_buf.as<u32>(), H); LAUNCHED();
+	invert_perm_kernel<<<GRID(H), TPB, 0, st>>>(rv, c.id_rank.as<u32>(), H); LAUNCHED();
+	return METRO_OK;
+}
+
+// Segmented sort: positions of every segment [segoff[a], +segcnt[a]) of the halos [lo, hi) ordered by (low 32 key bits, position).
+static int seg_sort(metro_ctx *ctx, const u64 *key, const u32 *segoff, const u32 *segcnt, i64 H, i64 lo, i64 hi, DevBuf &mid_b, DevBuf &long_b, u32 *sidx)
+{
+	cudaStream_t st = ctx->stream;
+	RES(mid_b, (H + 1) * 4); RES(long_b, (H + 1) * 4);
+	u32 *n_lists = reinterpret_cast<u32 *>(ctx->counters.as<u64>() + C_LISTS);
+	CUDA_TRY(ctx, cudaMemsetAsync(n_lists, 0, sizeof(u64), st));
+	// only the halos this rank owns have candidates (multi-GPU: 1/world of them)
+	seg_sort_small_kernel<<<(unsigned) div_up<i64>(std::max<i64>(hi - lo, 1) * 8, 256), 256, 0, st>>>(key, segoff, segcnt, lo, hi, sidx, mid_b.as<u32>(), long_b.as<u32>(), n_lists);
+	LAUNCHED();
+	seg_sort_mid_kernel<<<METRO_NUM_SMS_B200 * 4, 256, 0, st>>>(key, segoff, segcnt, mid_b.as<u32>(), n_lists, sidx);
+	LAUNCHED();
+	seg_sort_long_kernel<<<METRO_NUM_SMS_B200 * 2, 256, 0, st>>>(key, segoff, segcnt, long_b.as<u32>(), n_lists, sidx);
+	LAUNCHED();
+	return METRO_OK;
+}
+
+// Order n elements by (main ascending, sec ascending) without a radix sort: counting sort into the groups of `main` (one atomic per
+// element), then the segmented sort of every group on `sec`.  Groups are a handful of entries (the partners of one halo), so this
+// is one pass over the data + one pass of register sorts instead of 5-6 radix passes.  perm[j] = element at sorted position j;
+// key_sorted[j] = (main << 32) | sec of that element; segcnt / segoff = the groups.  W: 5 scratch buffers.
+static int group_by(metro_ctx *ctx, const u32 *main, const u32 *sec, i64 n_max, const u64 *nd, i64 H, i64 lo, i64 hi, DevBuf *W, DevBuf &segcnt_b,
+		    DevBuf &segoff_b, u32 *perm, u64 *key_sorted)
+{
+	cudaStream_t st = ctx->stream;
+	RES(segcnt_b, (H + 1) * 4); RES(segoff_b, (H + 1) * 4);
+	RES(W[0], (H + 1) * 4);                                    // cursor
+	RES(W[1], n_max * 4); RES(W[2], n_max * 8); RES(W[3], n_max * 4);   // slot_idx, slot_key, sidx
+	CUDA_TRY(ctx, cudaMemsetAsync(segcnt_b.p, 0, (size_t) (H + 1) * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(W[0].p, 0, (size_t) (H + 1) * 4, st));
+	u32 *segcnt = segcnt_b.as<u32>(), *segoff = segoff_b.as<u32>();
+	count_group_kernel<<<GRID(n_max), TPB, 0, st>>>(main, n_max, nd, segcnt); LAUNCHED();
+	TRY(scan_exclusive_u32(ctx, st, segcnt, segoff, H + 1, nullptr));
+	group_scatter_kernel<<<GRID(n_max), TPB, 0, st>>>(main, sec, n_max, nd, segoff, W[0].as<u32>(), W[1].as<u32>(), W[2].as<u64>()); LAUNCHED();
+	TRY(seg_sort(ctx, W[2].as<u64>(), segoff, segcnt, H, lo, hi, W[4], W[5], W[3].as<u32>()));
+	group_perm_kernel<<<GRID(n_max), TPB, 0, st>>>(W[3].as<u32>(), W[1].as<u32>(), W[2].as<u64>(), main, n_max, nd, perm, key_sorted); LAUNCHED();
 	return METRO_OK;
 }
 
 // Per-direction list (grouped by `main`, ascending ID of `other` inside a group) -> raw tree:
-// offsets per main halo, merit sort, tie quirk.  S = 8 scratch buffers.
-struct DirList { const u32 *main, *other; const i32 *nc, *tot; i64 n; };
-static int build_tree(metro_ctx *ctx, const DirList &L, i64 H_main, i64 own_lo, i64 own_hi, int T, const i32 *np_main, const i32 *np_other, int hbits,
+// offsets per main halo, merit sort, tie quirk.  S = 8 scratch buffers.  n_max: upper bound of the list length, *nd: the length.
+struct DirList { const u32 *main, *other; const i32 *nc, *tot; i64 n_max; const u64 *nd; };
+static int build_tree(metro_ctx *ctx, const DirList &L, i64 H_main, i64 own_lo, i64 own_hi, int T, const i32 *np_main, const i32 *np_other,
 		      DevBuf *S, DevBuf &segcnt_b, DevBuf &segoff_b, DevBuf &out_main, DevBuf &out_prog, DevBuf &out_nc, DevBuf &out_merit)
 {
 	cudaStream_t st = ctx->stream;
-	const i64 n = L.n;
+	const i64 n = L.n_max;
 	RES(segcnt_b, (H_main + 1) * 4); RES(segoff_b, (H_main + 1) * 4);
 	RES(out_main, n * 4); RES(out_prog, n * 4); RES(out_nc, n * T * 4); RES(out_merit, n * 4);
 	CUDA_TRY(ctx, cudaMemsetAsync(segcnt_b.p, 0, (size_t) (H_main + 1) * 4, st));
 	u32 *segcnt = segcnt_b.as<u32>(), *segoff = segoff_b.as<u32>();
-	if (n > 0) { count_by_kernel<<<GRID(n), TPB, 0, st>>>(L.main, n, segcnt); LAUNCHED(); }
+	if (n > 0) { count_by_kernel<<<GRID(n), TPB, 0, st>>>(L.main, L.nd, segcnt); LAUNCHED(); }
 	TRY(scan_exclusive_u32(ctx, st, segcnt, segoff, H_main + 1, nullptr));
 	if (n == 0) return METRO_OK;
 	RES(S[0], n * 4); RES(S[1], n * 8); RES(S[2], n * 8); RES(S[3], n * 4); RES(S[4], n * 4); RES(S[5], n * 4);
 	u32 *merit = S[0].as<u32>();
-	merit_key_kernel<<<GRID(n), TPB, 0, st>>>(L.main, L.other, L.tot, segoff, segcnt, np_main, np_other, n, merit, S[1].as<u64>(), S[3].as<u32>());
+	merit_key_kernel<<<GRID(n), TPB, 0, st>>>(L.main, L.other, L.tot, segoff, segcnt, np_main, np_other, L.nd, merit, S[1].as<u64>(), S[3].as<u32>());
 	LAUNCHED();
 	// order inside every segment: descending merit, ties by position (== the stable sort on (halo, ~merit))
 	u32 *sidx = S[4].as<u32>();
-	RES(S[6], (H_main + 1) * 4); RES(S[7], (H_main + 1) * 4);
-	u32 *n_lists = reinterpret_cast<u32 *>(ctx->counters.as<u64>() + 21);
-	CUDA_TRY(ctx, cudaMemsetAsync(n_lists, 0, sizeof(u64), st));
-	// only the halos this rank owns have candidates (multi-GPU: 1/world of them)
-	seg_sort_small_kernel<<<(unsigned) div_up<i64>(std::max<i64>(own_hi - own_lo, 1) * 8, 256), 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, own_lo, own_hi, sidx, S[6].as<u32>(),
-													   S[7].as<u32>(), n_lists);
-	LAUNCHED();
-	seg_sort_mid_kernel<<<METRO_NUM_SMS_B200 * 4, 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, S[6].as<u32>(), n_lists, sidx);
-	LAUNCHED();
-	seg_sort_long_kernel<<<METRO_NUM_SMS_B200 * 2, 256, 0, st>>>(S[1].as<u64>(), segoff, segcnt, S[7].as<u32>(), n_lists, sidx);
-	LAUNCHED();
-	(void) hbits;
-	tie_quirk_kernel<<<GRID(n), TPB, 0, st>>>(sidx, L.main, merit, segoff, n, S[5].as<u32>()); LAUNCHED();
-	emit_raw_kernel<<<GRID(n), TPB, 0, st>>>(S[5].as<u32>(), n, T, L.main, L.other, L.nc, merit, segcnt, out_main.as<u32>(),
+	TRY(seg_sort(ctx, S[1].as<u64>(), segoff, segcnt, H_main, own_lo, own_hi, S[6], S[7], sidx));
+	tie_quirk_kernel<<<GRID(n), TPB, 0, st>>>(sidx, L.main, merit, segoff, L.nd, S[5].as<u32>()); LAUNCHED();
+	emit_raw_kernel<<<GRID(n), TPB, 0, st>>>(S[5].as<u32>(), L.nd, T, L.main, L.other, L.nc, merit, segcnt, out_main.as<u32>(),
 						  out_prog.as<i32>(), out_nc.as<i32>(), out_merit.as<u32>());
 	LAUNCHED();
 	return METRO_OK;
 }
 
-// Records (hit key, count) -> distinct (A,B) pairs with per-type counts for both directions,
-// thresholded (AssignMap) and compacted in (A, ID(B)) order.  Outputs in O[0..4]:
-// kA u32[K], kB u32[K], kF i32[K*T] (counts by typeB), kK i32[K*T] (by typeA), ktot i32[K].
-static int merge_records(metro_ctx *ctx, const metro_params *prm, HitLayout hl, int hbits, const u64 *rec_key, const u32 *rec_cnt, i64 R,
-			 const u32 *rank1, DevBuf *O, i64 *K_out, i64 *P_out)
+// Records (hit key, count) -> distinct (A,B) pairs with per-type counts for both directions, thresholded (AssignMap) and compacted
+// in (A, ID(B)) order (backward: (B, ID(A)) order).  Outputs in O[0..4], sized for R entries:
+// kA u32, kB u32, kF i32[.*T] (counts by typeB), kK i32[.*T] (by typeA), ktot i32.  *cP / *cK (device): distinct pairs / kept pairs.
+static int merge_records(metro_ctx *ctx, const metro_params *prm, HitLayout hl, const u64 *rec_key, const u32 *rec_cnt, i64 R,
+			 const u32 *rank_other, bool backward, i64 H_main, i64 own_lo, i64 own_hi, DevBuf *O, u64 *cP, u64 *cK)
 {
 	cudaStream_t st = ctx->stream;
 	const int T = prm->nptypes;
 	DevBuf *S = ctx->scratch;
-	u64 *cnt = ctx->counters.as<u64>();
-	u64 tot = 0;
-	i64 P = 0;
-	RES(S[4], R * 8); RES(S[5], R * 8); RES(S[6], R * 4); RES(S[7], R * 4); RES(S[8], R * 4); RES(S[9], R * 4);
-	u32 *order = nullptr;
-	if (R > 0) {
-		rec_key_kernel<<<GRID(R), TPB, 0, st>>>(rec_key, R, hl, rank1, S[4].as<u64>(), S[6].as<u32>()); LAUNCHED();
-		u64 *rk;
-		TRY(sort_kv(ctx, S[4].as<u64>(), S[5].as<u64>(), S[6].as<u32>(), S[7].as<u32>(), R, 2 * hbits, &rk, &order));
-		head_flag_kernel<<<GRID(R), TPB, 0, st>>>(rk, R, S[8].as<u32>()); LAUNCHED();
-		TRY(scan_exclusive_u32(ctx, st, S[8].as<u32>(), S[9].as<u32>(), R, cnt + 5));
-		TRY(read_total(ctx, cnt + 5, &tot));
-		P = (i64) tot;
+	RES(O[0], R * 4); RES(O[1], R * 4); RES(O[2], R * T * 4); RES(O[3], R * T * 4); RES(O[4], R * 4);
+	if (R == 0) {
+		CUDA_TRY(ctx, cudaMemsetAsync(cP, 0, sizeof(u64), st));
+		CUDA_TRY(ctx, cudaMemsetAsync(cK, 0, sizeof(u64), st));
+		return METRO_OK;
 	}
-	RES(S[10], P * 4); RES(S[11], P * 4); RES(S[12], P * T * 4); RES(S[13], P * T * 4); RES(S[14], P * 4);
-	i64 K = 0;
-	if (P > 0) {
-		CUDA_TRY(ctx, cudaMemsetAsync(S[12].p, 0, (size_t) P * T * 4, st));
-		CUDA_TRY(ctx, cudaMemsetAsync(S[13].p, 0, (size_t) P * T * 4, st));
-		CUDA_TRY(ctx, cudaMemsetAsync(S[14].p, 0, (size_t) P * 4, st));
-		pair_merge_kernel<<<GRID(R), TPB, 0, st>>>(rec_key, rec_cnt, order, S[8].as<u32>(), S[9].as<u32>(), R, hl, T,
-							    S[10].as<u32>(), S[11].as<u32>(), S[12].as<i32>(), S[13].as<i32>(), S[14].as<i32>());
-		LAUNCHED();
-		// AssignMap threshold, ordered compaction
-		RES(S[15], P * 4); RES(S[16], P * 4);
-		keep_flag_kernel<<<GRID(P), TPB, 0, st>>>(S[14].as<i32>(), P, prm->min_part_cmp, S[15].as<u32>()); LAUNCHED();
-		TRY(scan_exclusive_u32(ctx, st, S[15].as<u32>(), S[16].as<u32>(), P, cnt + 5));
-		TRY(read_total(ctx, cnt + 5, &tot));
-		K = (i64) tot;
-	}
-	RES(O[0], K * 4); RES(O[1], K * 4); RES(O[2], K * T * 4); RES(O[3], K * T * 4); RES(O[4], K * 4);
-	if (K > 0) {
-		pair_compact_kernel<<<GRID(P), TPB, 0, st>>>(S[15].as<u32>(), S[16].as<u32>(), P, T, S[10].as<u32>(), S[11].as<u32>(), S[12].as<i32>(),
-							      S[13].as<i32>(), S[14].as<i32>(), O[0].as<u32>(), O[1].as<u32>(), O[2].as<i32>(),
-							      O[3].as<i32>(), O[4].as<i32>());
-		LAUNCHED();
-	}
-	*K_out = K; *P_out = P;
+	RES(S[4], R * 8); RES(S[5], R * 4); RES(S[6], R * 4); RES(S[7], R * 4); RES(S[8], R * 4); RES(S[9], R * 4);
+	rec_split_kernel<<<GRID(R), TPB, 0, st>>>(rec_key, R, hl, rank_other, backward ? 1 : 0, S[5].as<u32>(), S[6].as<u32>()); LAUNCHED();
+	u64 *rk = S[4].as<u64>();
+	u32 *order = S[7].as<u32>();
+	TRY(group_by(ctx, S[5].as<u32>(), S[6].as<u32>(), R, nullptr, H_main, own_lo, own_hi, S + 70, S[76], S[77], order, rk));
+	head_flag_kernel<<<GRID(R), TPB, 0, st>>>(rk, R, S[8].as<u32>()); LAUNCHED();
+	TRY(scan_exclusive_u32(ctx, st, S[8].as<u32>(), S[9].as<u32>(), R, cP));
+	// distinct pairs P <= R: everything below is sized by R and guarded by *cP
+	RES(S[10], R * 4); RES(S[11], R * 4); RES(S[12], R * T * 4); RES(S[13], R * T * 4); RES(S[14], R * 4);
+	CUDA_TRY(ctx, cudaMemsetAsync(S[12].p, 0, (size_t) R * T * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(S[13].p, 0, (size_t) R * T * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(S[14].p, 0, (size_t) R * 4, st));
+	pair_merge_kernel<<<GRID(R), TPB, 0, st>>>(rec_key, rec_cnt, order, S[8].as<u32>(), S[9].as<u32>(), R, hl, T,
+						    S[10].as<u32>(), S[11].as<u32>(), S[12].as<i32>(), S[13].as<i32>(), S[14].as<i32>());
+	LAUNCHED();
+	// AssignMap threshold, ordered compaction
+	RES(S[15], R * 4); RES(S[16], R * 4);
+	keep_flag_kernel<<<GRID(R), TPB, 0, st>>>(S[14].as<i32>(), R, cP, prm->min_part_cmp, S[15].as<u32>()); LAUNCHED();
+	TRY(scan_exclusive_u32(ctx, st, S[15].as<u32>(), S[16].as<u32>(), R, cK));
+	pair_compact_kernel<<<GRID(R), TPB, 0, st>>>(S[15].as<u32>(), S[16].as<u32>(), R, T, S[10].as<u32>(), S[11].as<u32>(), S[12].as<i32>(),
+						      S[13].as<i32>(), S[14].as<i32>(), O[0].as<u32>(), O[1].as<u32>(), O[2].as<i32>(),
+						      O[3].as<i32>(), O[4].as<i32>());
+	LAUNCHED();
 	return METRO_OK;
 }
 
@@ -508,49 +560,49 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	DevResult &res = ctx->res;
 	u64 *cnt = ctx->counters.as<u64>();
 	HitLayout hl = {KL.halo_bits, KL.type_bits};
-	const int hbits = KL.halo_bits;
 
 	// halo-ID ranks (std::map iteration order of indexCommon is ascending halo ID, not file order)
-	TRY(id_ranks(ctx, c0, S[2], S + 40));
-	TRY(id_ranks(ctx, c1, S[3], S + 40));
-	const u32 *rank0 = S[2].as<u32>(), *rank1 = S[3].as<u32>();
+	TRY(id_ranks(ctx, c0, S + 40));
+	TRY(id_ranks(ctx, c1, S + 40));
+	const u32 *rank0 = c0.id_rank.as<u32>(), *rank1 = c1.id_rank.as<u32>();
 
-	// 1.-2. distinct pairs above the threshold: forward set -> S[17..21], backward set -> S[64..68]
-	i64 K = 0, P = 0, KB = 0, PB = 0;
-	TRY(merge_records(ctx, prm, hl, hbits, recA_key, recA_cnt, RA, rank1, S + 17, &K, &P));
-	res.info.n_pairs = P;
-	DevBuf *B = S + 17;
-	KB = K;
-	if (recB_key != recA_key) {
-		TRY(merge_records(ctx, prm, hl, hbits, recB_key, recB_cnt, RB, rank1, S + 64, &KB, &PB));
-		B = S + 64;
-	}
-
-	// 3. forward raw tree (locMTrees[0])
-	DirList fwd = {S[17].as<u32>(), S[18].as<u32>(), S[19].as<i32>(), S[21].as<i32>(), K};
+	// 1.-2. distinct pairs above the threshold: forward set -> S[17..21] in (A, ID(B)) order
 	i64 b_lo = 0, b_hi = H1;                                  // catalogue-1 halos whose backward trees this rank builds
 	comm_owned_range(ctx, H1, &b_lo, &b_hi);
-	TRY(build_tree(ctx, fwd, H0, a_lo, a_hi, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), hbits, S + 40, S[22], S[23], S[24], res.raw_prog[0],
+	TRY(merge_records(ctx, prm, hl, recA_key, recA_cnt, RA, rank1, false, H0, a_lo, a_hi, S + 17, cnt + C_P_FWD, cnt + C_K_FWD));
+	const bool sharded = recB_key != recA_key;
+	const i64 KB_max = sharded ? RB : RA;                    // upper bound of the backward list
+	const u64 *cKB = sharded ? cnt + C_K_BWD : cnt + C_K_FWD;
+
+	// 3. forward raw tree (locMTrees[0])
+	DirList fwd = {S[17].as<u32>(), S[18].as<u32>(), S[19].as<i32>(), S[21].as<i32>(), RA, cnt + C_K_FWD};
+	TRY(build_tree(ctx, fwd, H0, a_lo, a_hi, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), S + 40, S[22], S[23], S[24], res.raw_prog[0],
 		       res.raw_ncommon[0], res.raw_merit[0]));
-	// 4. backward raw tree (locMTrees[1]): same pairs ordered by (B, ID(A)), by-type counts of the 0 side
-	RES(S[25], KB * 4); RES(S[26], KB * 4); RES(S[27], KB * T * 4); RES(S[28], KB * 4);
-	if (KB > 0) {
-		RES(S[40], KB * 8); RES(S[41], KB * 8); RES(S[42], KB * 4); RES(S[43], KB * 4);
-		bwd_key_kernel<<<GRID(KB), TPB, 0, st>>>(B[0].as<u32>(), B[1].as<u32>(), rank0, hbits, KB, S[40].as<u64>(), S[42].as<u32>()); LAUNCHED();
-		u64 *rk; u32 *perm;
-		TRY(sort_kv(ctx, S[40].as<u64>(), S[41].as<u64>(), S[42].as<u32>(), S[43].as<u32>(), KB, 2 * hbits, &rk, &perm));
-		gather_dir_kernel<<<GRID(KB), TPB, 0, st>>>(perm, KB, T, B[1].as<u32>(), B[0].as<u32>(), B[3].as<i32>(), B[4].as<i32>(),
-							     S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>());
-		LAUNCHED();
+	// 4. backward raw tree (locMTrees[1]): the pairs ordered by (B, ID(A)), by-type counts of the 0 side
+	DirList bwd;
+	if (sharded) {
+		// the records routed to owner(B) are merged in backward order right away: no second sort
+		TRY(merge_records(ctx, prm, hl, recB_key, recB_cnt, RB, rank0, true, H1, b_lo, b_hi, S + 64, cnt + C_P_BWD, cnt + C_K_BWD));
+		bwd = {S[65].as<u32>(), S[64].as<u32>(), S[67].as<i32>(), S[68].as<i32>(), RB, cKB};
+	} else {
+		RES(S[25], KB_max * 4); RES(S[26], KB_max * 4); RES(S[27], KB_max * T * 4); RES(S[28], KB_max * 4);
+		if (KB_max > 0) {
+			RES(S[40], KB_max * 4); RES(S[41], KB_max * 8); RES(S[42], KB_max * 4);
+			rank_of_kernel<<<GRID(KB_max), TPB, 0, st>>>(S[17].as<u32>(), rank0, KB_max, cKB, S[40].as<u32>()); LAUNCHED();
+			u32 *perm = S[42].as<u32>();
+			TRY(group_by(ctx, S[18].as<u32>(), S[40].as<u32>(), KB_max, cKB, H1, b_lo, b_hi, S + 70, S[76], S[77], perm, S[41].as<u64>()));
+			gather_dir_kernel<<<GRID(KB_max), TPB, 0, st>>>(perm, cKB, T, S[18].as<u32>(), S[17].as<u32>(), S[20].as<i32>(), S[21].as<i32>(),
+									 S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>());
+			LAUNCHED();
+		}
+		bwd = {S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>(), KB_max, cKB};
 	}
-	DirList bwd = {S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>(), KB};
-	TRY(build_tree(ctx, bwd, H1, b_lo, b_hi, T, c1.npart_tot.as<i32>(), c0.npart_tot.as<i32>(), hbits, S + 40, S[29], S[30], S[31], res.raw_prog[1],
+	TRY(build_tree(ctx, bwd, H1, b_lo, b_hi, T, c1.npart_tot.as<i32>(), c0.npart_tot.as<i32>(), S + 40, S[29], S[30], S[31], res.raw_prog[1],
 		       res.raw_ncommon[1], res.raw_merit[1]));
-	res.info.raw_count[0] = K; res.info.raw_count[1] = KB;
 	for (int d = 0; d < 2; d++) {
 		const i64 H = d ? H1 : H0;
 		RES(res.raw_off[d], (H + 1) * 8);
-		off32_to_64_kernel<<<GRID(H + 1), TPB, 0, st>>>((d ? S[30] : S[23]).as<u32>(), H, (u64) (d ? KB : K), res.raw_off[d].as<i64>());
+		off32_to_64_kernel<<<GRID(H + 1), TPB, 0, st>>>((d ? S[30] : S[23]).as<u32>(), H, d ? cKB : cnt + C_K_FWD, res.raw_off[d].as<i64>());
 		LAUNCHED();
 	}
 
@@ -559,15 +611,15 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	best_desc_kernel<<<GRID(H1), TPB, 0, st>>>(S[30].as<u32>(), S[29].as<u32>(), res.raw_prog[1].as<i32>(), H1, S[32].as<i32>()); LAUNCHED();
 	// multi-GPU: the owner of each catalogue-1 halo knows its best descendant, everybody needs it
 	TRY(comm_allreduce_max_i32(ctx, S[32].as<i32>(), H1));
-	RES(S[33], K * 4); RES(S[34], K * 4); RES(S[35], (H0 + 1) * 4); RES(S[36], (H0 + 1) * 4);
+	RES(S[33], RA * 4); RES(S[34], RA * 4); RES(S[35], (H0 + 1) * 4); RES(S[36], (H0 + 1) * 4);
 	u32 *cntc = S[35].as<u32>(), *cstart = S[36].as<u32>();
 	CUDA_TRY(ctx, cudaMemsetAsync(cntc, 0, (size_t) (H0 + 1) * 4, st));
-	CUDA_TRY(ctx, cudaMemsetAsync(cnt + 4, 0, sizeof(u64), st));
-	if (K > 0) {
-		clean_flag_kernel<<<GRID(K), TPB, 0, st>>>(S[24].as<u32>(), res.raw_prog[0].as<i32>(), K, S[32].as<i32>(), c0.halo_id.as<u64>(),
-							    S[33].as<u32>(), cntc);
+	CUDA_TRY(ctx, cudaMemsetAsync(cnt + C_UNTRACKED, 0, sizeof(u64), st));
+	if (RA > 0) {
+		clean_flag_kernel<<<GRID(RA), TPB, 0, st>>>(S[24].as<u32>(), res.raw_prog[0].as<i32>(), RA, cnt + C_K_FWD, S[32].as<i32>(), c0.halo_id.as<u64>(),
+							     S[33].as<u32>(), cntc);
 		LAUNCHED();
-		TRY(scan_exclusive_u32(ctx, st, S[33].as<u32>(), S[34].as<u32>(), K, nullptr));
+		TRY(scan_exclusive_u32(ctx, st, S[33].as<u32>(), S[34].as<u32>(), RA, nullptr));
 	}
 	TRY(scan_exclusive_u32(ctx, st, cntc, cstart, H0 + 1, nullptr));
 	// orphan / token rule
@@ -584,26 +636,22 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	DevBuf *Q = S + 48;              // second scratch bank
 	RES(Q[0], (H0 + 1) * 4); RES(Q[1], (H0 + 1) * 4); RES(Q[2], (H0 + 1) * 4);
 	u32 *coff = Q[0].as<u32>(), *tscan = Q[1].as<u32>(), *kscan = Q[2].as<u32>();
-	TRY(scan_exclusive_u32(ctx, st, nfin, coff, H0 + 1, cnt + 5));
-	TRY(scan_exclusive_u32(ctx, st, has_tree, tscan, H0 + 1, cnt + 6));
+	TRY(scan_exclusive_u32(ctx, st, nfin, coff, H0 + 1, cnt + C_CLEAN));
+	TRY(scan_exclusive_u32(ctx, st, has_tree, tscan, H0 + 1, cnt + C_TREES));
 	// the token list is global (every rank appends all token halos in the shift): OR the per-rank flags
 	RES(Q[11], (H0 + 1) * 4);
 	u32 *gtoken = Q[11].as<u32>();
 	CUDA_TRY(ctx, cudaMemcpyAsync(gtoken, token, (size_t) (H0 + 1) * 4, cudaMemcpyDeviceToDevice, st));
 	TRY(comm_allreduce_max_i32(ctx, reinterpret_cast<i32 *>(gtoken), H0));
-	TRY(scan_exclusive_u32(ctx, st, gtoken, kscan, H0 + 1, cnt + 7));
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, cnt, 8 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(ctx, cudaStreamSynchronize(st));
-	const i64 C = (i64) ctx->h_counters[5], NT = (i64) ctx->h_counters[6], NK = (i64) ctx->h_counters[7];
-	res.info.n_untracked = (i64) ctx->h_counters[4];
-	res.info.clean_count = C; res.info.n_trees = NT; res.info.n_tokens = NK;
+	TRY(scan_exclusive_u32(ctx, st, gtoken, kscan, H0 + 1, cnt + C_TOKENS));
 
-	// clean list grouped by A (kept entries in first-sort order, or the single token entry)
-	RES(Q[3], C * 4); RES(Q[4], C * 4); RES(Q[5], C * T * 4); RES(Q[6], C * 4);
-	if (K > 0) {
-		clean_fill_kernel<<<GRID(K), TPB, 0, st>>>(S[33].as<u32>(), S[34].as<u32>(), K, T, S[24].as<u32>(), res.raw_prog[0].as<i32>(),
-							    res.raw_ncommon[0].as<i32>(), cstart, coff, Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(),
-							    Q[6].as<i32>());
+	// clean list grouped by A (kept entries in first-sort order, or the single token entry): C <= K + tokens <= RA + H0 entries
+	const i64 C_max = RA + H0;
+	RES(Q[3], C_max * 4); RES(Q[4], C_max * 4); RES(Q[5], C_max * T * 4); RES(Q[6], C_max * 4);
+	if (RA > 0) {
+		clean_fill_kernel<<<GRID(RA), TPB, 0, st>>>(S[33].as<u32>(), S[34].as<u32>(), cnt + C_K_FWD, T, S[24].as<u32>(), res.raw_prog[0].as<i32>(),
+							     res.raw_ncommon[0].as<i32>(), cstart, coff, Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(),
+							     Q[6].as<i32>());
 		LAUNCHED();
 	}
 	if (H0 > 0) {
@@ -612,16 +660,26 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 		LAUNCHED();
 	}
 	// second SortByMerit (:627-628) with iM = position in the kept list
-	DirList cl = {Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(), Q[6].as<i32>(), C};
-	TRY(build_tree(ctx, cl, H0, a_lo, a_hi, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), hbits, S + 40, Q[7], Q[8], Q[9], res.clean_prog,
+	DirList cl = {Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(), Q[6].as<i32>(), C_max, cnt + C_CLEAN};
+	TRY(build_tree(ctx, cl, H0, a_lo, a_hi, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), S + 40, Q[7], Q[8], Q[9], res.clean_prog,
 		       res.clean_ncommon, Q[10]));
-	RES(res.tree_main, NT * 4); RES(res.tree_orphan, NT); RES(res.tree_off, (NT + 1) * 8); RES(res.token_halo, NK * 4);
+	// trees and tokens: at most one per catalogue-0 halo
+	RES(res.tree_main, H0 * 4); RES(res.tree_orphan, H0); RES(res.tree_off, (H0 + 1) * 8); RES(res.token_halo, H0 * 4);
 	if (H0 > 0) {
 		tree_emit_kernel<<<GRID(H0), TPB, 0, st>>>(has_tree, tscan, token, coff, H0, res.tree_main.as<i32>(), res.tree_orphan.as<u8>(),
 							    res.tree_off.as<i64>());
 		LAUNCHED();
 		token_emit_kernel<<<GRID(H0), TPB, 0, st>>>(gtoken, kscan, H0, res.token_halo.as<i32>()); LAUNCHED();
 	}
-	set_i64_kernel<<<1, 1, 0, st>>>(res.tree_off.as<i64>() + NT, C); LAUNCHED();
+	tree_off_end_kernel<<<1, 1, 0, st>>>(res.tree_off.as<i64>(), cnt + C_TREES, cnt + C_CLEAN); LAUNCHED();
+	// the one host round trip of the stage: sizes for the caller
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, cnt, 40 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	const u64 *h = ctx->h_counters;
+	res.info.n_pairs = (i64) h[C_P_FWD];
+	res.info.raw_count[0] = (i64) h[C_K_FWD];
+	res.info.raw_count[1] = (i64) (sharded ? h[C_K_BWD] : h[C_K_FWD]);
+	res.info.n_untracked = (i64) h[C_UNTRACKED];
+	res.info.clean_count = (i64) h[C_CLEAN]; res.info.n_trees = (i64) h[C_TREES]; res.info.n_tokens = (i64) h[C_TOKENS];
 	return METRO_OK;
 }

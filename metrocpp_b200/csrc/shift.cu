@@ -88,7 +88,7 @@ __global__ void token_tuple_emit_kernel(const u64 *pid, const u32 *halo, const u
 	for (int r = 0; r < rep; r++) {
 		opid[d + r] = pid[i];
 		ohalo[d + r] = halo_base + (u32) slot[halo[i]];
-		otype[d + r] = type ? type[i] : (u8) 1;
+		if (otype) otype[d + r] = type ? type[i] : (u8) 1;
 	}
 }
 
@@ -131,27 +131,49 @@ int stage_shift(metro_ctx *ctx, const metro_params *prm)
 		extra = ctx->h_counters[18];
 	}
 	const i64 NN = N1 + (i64) extra * rep, HH = H1 + NK;
-	// new catalogue 0, built in fresh buffers (catalogue 1 may be borrowed memory)
 	DevCatalogue n0;
-	n0.n_halos = HH; n0.n_tuples = NN;
-	TRY(dev_reserve(ctx, n0.halo_id, (size_t) HH * 8 + 8)); TRY(dev_reserve(ctx, n0.npart, (size_t) HH * T * 4 + 8));
-	TRY(dev_reserve(ctx, n0.npart_tot, (size_t) HH * 4 + 8)); TRY(dev_reserve(ctx, n0.n_orphan_steps, (size_t) HH * 4 + 8));
-	TRY(dev_reserve(ctx, n0.is_token, (size_t) HH + 8));
-	TRY(dev_reserve(ctx, n0.pid, (size_t) NN * 8 + 8)); TRY(dev_reserve(ctx, n0.halo, (size_t) NN * 4 + 8));
-	TRY(dev_reserve(ctx, n0.type, (size_t) NN + 8));
-	if (H1 > 0) {
-		CUDA_TRY(ctx, cudaMemcpyAsync(n0.halo_id.p, c1.halo_id.p, (size_t) H1 * 8, cudaMemcpyDeviceToDevice, st));
-		CUDA_TRY(ctx, cudaMemcpyAsync(n0.npart.p, c1.npart.p, (size_t) H1 * T * 4, cudaMemcpyDeviceToDevice, st));
-		CUDA_TRY(ctx, cudaMemcpyAsync(n0.npart_tot.p, c1.npart_tot.p, (size_t) H1 * 4, cudaMemcpyDeviceToDevice, st));
-		CUDA_TRY(ctx, cudaMemcpyAsync(n0.n_orphan_steps.p, c1.n_orphan_steps.p, (size_t) H1 * 4, cudaMemcpyDeviceToDevice, st));
-		CUDA_TRY(ctx, cudaMemcpyAsync(n0.is_token.p, c1.is_token.p, (size_t) H1, cudaMemcpyDeviceToDevice, st));
+	const bool move = c1.b_pid == nullptr;
+	if (move) {
+		// Catalogue 1 owns its buffers: they BECOME catalogue 0 - its halos and tuples stay where they are, the token halos and
+		// token tuples are appended behind them (uploads leave head room for exactly this), nothing is copied, allocated or freed.
+		// A chain step of the reference re-inserts every particle of snapshot 1 into a new map here (src/utils.cpp:272-278).
+		TRY(dev_reserve_keep(ctx, c1.halo_id, (size_t) HH * 8 + 8, (size_t) H1 * 8)); TRY(dev_reserve_keep(ctx, c1.npart, (size_t) HH * T * 4 + 8, (size_t) H1 * T * 4));
+		TRY(dev_reserve_keep(ctx, c1.npart_tot, (size_t) HH * 4 + 8, (size_t) H1 * 4));
+		TRY(dev_reserve_keep(ctx, c1.n_orphan_steps, (size_t) HH * 4 + 8, (size_t) H1 * 4));
+		TRY(dev_reserve_keep(ctx, c1.is_token, (size_t) HH + 8, (size_t) H1));
+		TRY(dev_reserve_keep(ctx, c1.pid, (size_t) NN * 8 + 8, (size_t) N1 * 8)); TRY(dev_reserve_keep(ctx, c1.halo, (size_t) NN * 4 + 64, (size_t) N1 * 4));
+		if (c1.type.p) TRY(dev_reserve_keep(ctx, c1.type, (size_t) NN + 8, (size_t) N1));
+		else if (c0.d_type() && extra > 0) {
+			// catalogue 1 came without a type column (all 1), the token tuples carry types: materialise the column
+			TRY(dev_reserve(ctx, c1.type, (size_t) NN + 8));
+			if (N1 > 0) { fill_u8_kernel<<<GRID(N1), TPB, 0, st>>>(c1.type.as<u8>(), N1, 1); LAUNCHED(); }
+		}
+		n0 = c1;                                                 // the buffers move with the struct
+		n0.id_rank = DevBuf(); n0.id_rank_gen = 0; n0.id_rank_n = -1;
+		n0.n_halos = HH; n0.n_tuples = NN;
+	} else {
+		// catalogue 1 is borrowed device memory (metro_catalogue_adopt_device): the new catalogue 0 is built in fresh buffers
+		n0.n_halos = HH; n0.n_tuples = NN;
+		TRY(dev_reserve(ctx, n0.halo_id, (size_t) HH * 8 + 8)); TRY(dev_reserve(ctx, n0.npart, (size_t) HH * T * 4 + 8));
+		TRY(dev_reserve(ctx, n0.npart_tot, (size_t) HH * 4 + 8)); TRY(dev_reserve(ctx, n0.n_orphan_steps, (size_t) HH * 4 + 8));
+		TRY(dev_reserve(ctx, n0.is_token, (size_t) HH + 8));
+		TRY(dev_reserve(ctx, n0.pid, (size_t) NN * 8 + 8)); TRY(dev_reserve(ctx, n0.halo, (size_t) NN * 4 + 64));
+		TRY(dev_reserve(ctx, n0.type, (size_t) NN + 8));
+		if (H1 > 0) {
+			CUDA_TRY(ctx, cudaMemcpyAsync(n0.halo_id.p, c1.halo_id.p, (size_t) H1 * 8, cudaMemcpyDeviceToDevice, st));
+			CUDA_TRY(ctx, cudaMemcpyAsync(n0.npart.p, c1.npart.p, (size_t) H1 * T * 4, cudaMemcpyDeviceToDevice, st));
+			CUDA_TRY(ctx, cudaMemcpyAsync(n0.npart_tot.p, c1.npart_tot.p, (size_t) H1 * 4, cudaMemcpyDeviceToDevice, st));
+			CUDA_TRY(ctx, cudaMemcpyAsync(n0.n_orphan_steps.p, c1.n_orphan_steps.p, (size_t) H1 * 4, cudaMemcpyDeviceToDevice, st));
+			CUDA_TRY(ctx, cudaMemcpyAsync(n0.is_token.p, c1.is_token.p, (size_t) H1, cudaMemcpyDeviceToDevice, st));
+		}
+		if (N1 > 0) {
+			CUDA_TRY(ctx, cudaMemcpyAsync(n0.pid.p, c1.d_pid(), (size_t) N1 * 8, cudaMemcpyDeviceToDevice, st));
+			CUDA_TRY(ctx, cudaMemcpyAsync(n0.halo.p, c1.d_halo(), (size_t) N1 * 4, cudaMemcpyDeviceToDevice, st));
+			if (c1.d_type()) CUDA_TRY(ctx, cudaMemcpyAsync(n0.type.p, c1.d_type(), (size_t) N1, cudaMemcpyDeviceToDevice, st));
+			else { fill_u8_kernel<<<GRID(N1), TPB, 0, st>>>(n0.type.as<u8>(), N1, 1); LAUNCHED(); }
+		}
 	}
-	if (N1 > 0) {
-		CUDA_TRY(ctx, cudaMemcpyAsync(n0.pid.p, c1.d_pid(), (size_t) N1 * 8, cudaMemcpyDeviceToDevice, st));
-		CUDA_TRY(ctx, cudaMemcpyAsync(n0.halo.p, c1.d_halo(), (size_t) N1 * 4, cudaMemcpyDeviceToDevice, st));
-		if (c1.d_type()) CUDA_TRY(ctx, cudaMemcpyAsync(n0.type.p, c1.d_type(), (size_t) N1, cudaMemcpyDeviceToDevice, st));
-		else { fill_u8_kernel<<<GRID(N1), TPB, 0, st>>>(n0.type.as<u8>(), N1, 1); LAUNCHED(); }
-	}
+	n0.b_pid = nullptr; n0.b_halo = nullptr; n0.b_type = nullptr;
 	if (NK > 0) {
 		token_halo_emit_kernel<<<GRID(NK), TPB, 0, st>>>(res.token_halo.as<i32>(), NK, T, c0.halo_id.as<u64>(), c0.npart.as<i32>(),
 								  c0.npart_tot.as<i32>(), c0.n_orphan_steps.as<i32>(), n0.halo_id.as<u64>() + H1,
@@ -161,7 +183,7 @@ int stage_shift(metro_ctx *ctx, const metro_params *prm)
 		if (extra > 0) {
 			token_tuple_emit_kernel<<<GRID(N0), TPB, 0, st>>>(c0.d_pid(), c0.d_halo(), c0.d_type(), N0, S[0].as<i32>(), S[1].as<u32>(),
 									   S[2].as<u32>(), rep, (u32) H1, n0.pid.as<u64>() + N1, n0.halo.as<u32>() + N1,
-									   n0.type.as<u8>() + N1);
+									   n0.type.p ? n0.type.as<u8>() + N1 : nullptr);
 			LAUNCHED();
 		}
 	}
@@ -176,13 +198,22 @@ int stage_shift(metro_ctx *ctx, const metro_params *prm)
 	if (R.cat1 && R.gen == c1.gen) { R.cat0 = true; R.gen = n0.gen; R.half0 = R.half1; R.half1 = 1 - R.half0; R.tail0 = N1; }
 	else R.cat0 = false;
 	R.cat1 = false;
-	// release the old catalogues (owned buffers only)
-	DevBuf *old0[] = {&c0.halo_id, &c0.npart, &c0.npart_tot, &c0.n_orphan_steps, &c0.is_token, &c0.pid, &c0.halo, &c0.type};
-	for (DevBuf *b : old0) dev_free(*b);
-	DevBuf *old1[] = {&c1.halo_id, &c1.npart, &c1.npart_tot, &c1.n_orphan_steps, &c1.is_token, &c1.pid, &c1.halo, &c1.type};
-	for (DevBuf *b : old1) dev_free(*b);
-	ctx->cat[0] = n0;
-	ctx->cat[1] = DevCatalogue();
+	if (move) {
+		// the buffers of the old catalogue 0 stay with slot 1 for the next upload (no free, no allocation in a chain step)
+		DevCatalogue keep;
+		keep.halo_id = c0.halo_id; keep.npart = c0.npart; keep.npart_tot = c0.npart_tot; keep.n_orphan_steps = c0.n_orphan_steps; keep.is_token = c0.is_token;
+		keep.pid = c0.pid; keep.halo = c0.halo; keep.type = c0.type; keep.id_rank = c0.id_rank;
+		ctx->cat[0] = n0;
+		ctx->cat[1] = keep;
+	} else {
+		// release the old catalogues (owned buffers only)
+		DevBuf *old0[] = {&c0.halo_id, &c0.npart, &c0.npart_tot, &c0.n_orphan_steps, &c0.is_token, &c0.pid, &c0.halo, &c0.type, &c0.id_rank};
+		for (DevBuf *b : old0) dev_free(*b);
+		DevBuf *old1[] = {&c1.halo_id, &c1.npart, &c1.npart_tot, &c1.n_orphan_steps, &c1.is_token, &c1.pid, &c1.halo, &c1.type, &c1.id_rank};
+		for (DevBuf *b : old1) dev_free(*b);
+		ctx->cat[0] = n0;
+		ctx->cat[1] = DevCatalogue();
+	}
 	res.valid = false;
 	return METRO_OK;
 }

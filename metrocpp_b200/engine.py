@@ -100,8 +100,9 @@ class MetroEngine:
             raise MetroError(rc, self.lib.metro_last_error(self.h).decode())
 
     # -- catalogues (locHalos[slot], locMapParts[slot]) ---------------------------------------
-    def upload(self, slot: int, prm: Params, cat: HostCatalogue, device_ptrs: tuple | None = None, halo_offset=None):
-        """halo_offset (int64[H+1]): tuples are grouped by halo (the locParts layout); cat.halo is then not sent."""
+    def upload(self, slot: int, prm: Params, cat: HostCatalogue, device_ptrs: tuple | None = None, halo_offset=None, pid32=None, pid_base: int = 0):
+        """halo_offset (int64[H+1]): tuples are grouped by halo (the locParts layout); cat.halo is then not sent.
+        pid32 (uint32[N], with halo_offset): particle IDs as 32-bit offsets from pid_base; cat.pid is then not sent."""
         T = prm.nptypes
         c = _lib.Catalogue()
         keep = []
@@ -111,7 +112,8 @@ class MetroEngine:
                 assert a.shape == shape, (a.shape, shape)
             keep.append(a)
             return a.ctypes.data
-        H, N = cat.n_halos, cat.n_tuples
+        H = cat.n_halos
+        N = int(pid32.shape[0]) if pid32 is not None else cat.n_tuples
         c.n_halos, c.n_tuples = H, N
         c.halo_id = arr(cat.halo_id, np.uint64)
         c.npart = arr(cat.npart, np.int32, (H, T))
@@ -120,6 +122,12 @@ class MetroEngine:
         if device_ptrs is not None:
             c.pid, c.halo, c.type = device_ptrs
             self._check(self.lib.metro_catalogue_adopt_device(self.h, slot, C.byref(prm), C.byref(c)))
+        elif pid32 is not None:
+            assert halo_offset is not None
+            c.pid, c.halo = None, None
+            c.type = arr(cat.type, np.uint8) if cat.type is not None else None
+            off = arr(halo_offset, np.int64, (H + 1,))
+            self._check(self.lib.metro_catalogue_upload_csr32(self.h, slot, C.byref(prm), C.byref(c), arr(pid32, np.uint32), pid_base, off))
         else:
             c.pid = arr(cat.pid, np.uint64)
             c.type = arr(cat.type, np.uint8) if cat.type is not None else None
@@ -190,7 +198,7 @@ class MetroEngine:
     def timings(self) -> dict:
         t = _lib.Timings()
         self._check(self.lib.metro_get_timings(self.h, C.byref(t)))
-        d = {k: getattr(t, k) for k in ("total", "pack_hist", "sort", "join", "select", "exchange", "sort_launches", "total_launches", "path", "resident")}
+        d = {k: getattr(t, k) for k in ("total", "pack_hist", "sort", "join", "select", "exchange", "sort_launches", "total_launches", "path", "resident", "exchange_sendrecv")}
         d["sort_pass_ms"] = list(t.sort_pass_ms)
         return d
 

@@ -406,7 +406,45 @@ void IOSettings::ReadParticles()
 		T.haloOffset.clear();
 	}
 	if (dropped) fprintf(stderr, "WARNING: %zu particle lines belong to halo IDs that are not in the halo catalogue; ignored\n", dropped);
+	if (totTask > 1) ShardByParticleId(T, H.size());
 	slotDirty[iUseCat] = true;
+}
+
+// Multi-rank runs: every rank reads ALL chunk files of the snapshot (so it holds the full halo table, with the catalogue
+// npart the merit needs) and keeps the tuples of its particle-ID range: all memberships of a particle then sit on one GPU and the
+// join needs no exchange.  The range width is fixed by the first (latest) snapshot: ceil(max ID / ranks) rounded up to a power of two
+// share, the same on every rank and for every later snapshot (IDs above the last boundary stay with the last rank).
+// (The reference hands nChunks / totTask chunk FILES to each task instead, src/IOSettings.cpp:459-460, and ships buffer halos between
+// the tasks afterwards.)
+void IOSettings::ShardByParticleId(TupleSoA &T, size_t nHalos)
+{
+	const size_t N = T.pid.size();
+	if (pidShardWidth == 0) {
+		uint64_t mx = 0;
+		for (size_t i = 0; i < N; i++) mx = T.pid[i] > mx ? T.pid[i] : mx;
+		uint64_t span = 1;
+		while (span <= mx) span <<= 1;
+		pidShardWidth = (span + (uint64_t) totTask - 1) / (uint64_t) totTask;
+		if (pidShardWidth == 0) pidShardWidth = 1;
+	}
+	const uint64_t lo = pidShardWidth * (uint64_t) locTask;
+	const bool last = locTask == totTask - 1;
+	const uint64_t hi = lo + pidShardWidth;
+	const bool grouped = T.haloOffset.size() == nHalos + 1;
+	std::vector<int64_t> cnt(grouped ? nHalos + 1 : 0, 0);
+	size_t w = 0;
+	for (size_t i = 0; i < N; i++) {
+		const uint64_t p = T.pid[i];
+		if (p < lo || (!last && p >= hi)) continue;
+		T.pid[w] = p; T.halo[w] = T.halo[i]; T.type[w] = T.type[i];
+		if (grouped) cnt[T.halo[i] + 1]++;
+		w++;
+	}
+	T.pid.resize(w); T.halo.resize(w); T.type.resize(w);
+	if (grouped) {
+		for (size_t h = 0; h < nHalos; h++) cnt[h + 1] += cnt[h];
+		T.haloOffset = cnt;
+	}
 }
 
 void IOSettings::WriteTree(int iThisCat)
@@ -433,6 +471,7 @@ void IOSettings::WriteTree(int iThisCat)
 
 void IOSettings::WriteLog(int iNum, float seconds)
 {
+	if (locTask != 0) return;                                   // one timing log per run (the reference writes it on rank 0, src/main.cpp:156)
 	if (iNum == 0) {
 		const std::string name = pathOutput + "timing_log." + std::to_string(totTask) + "." + std::to_string(nChunks) + ".b200.txt";
 		fileLogOut.open(name);

@@ -27,6 +27,7 @@ public:
 
 private:
 	void InitFromCfgFile(const std::string &key, const std::string &value);
+	void ShardByParticleId(struct TupleSoA &T, size_t nHalos);   // multi-rank: keep this rank's particle-ID range
 	std::ofstream fileLogOut;
 	std::vector<float> logTime;
 };

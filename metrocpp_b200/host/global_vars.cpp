@@ -4,6 +4,8 @@
 #include <cstdlib>
 
 int locTask = 0, totTask = 1;
+int gpuDevice = 0;
+uint64_t pidShardWidth = 0;
 std::vector<std::vector<Halo>> locHalos;
 std::vector<TupleSoA> locTuples;
 std::vector<std::vector<MergerTree>> locMTrees;
@@ -28,7 +30,7 @@ void InitLocVariables(bool needGpu)
 	locTuples.assign(2, {});
 	locMTrees.assign(2, {});
 	if (needGpu && !gpuCtx) {
-		int rc = metro_ctx_create(0, &gpuCtx);
+		int rc = metro_ctx_create(gpuDevice, &gpuCtx);
 		if (rc != METRO_OK) Fatal(std::string("cannot create the GPU context: ") + metro_last_error(nullptr));
 	}
 }

@@ -40,7 +40,9 @@ struct TupleSoA {                      // one catalogue's "lines of the _particl
 	}
 };
 
-extern int locTask, totTask;
+extern int locTask, totTask;                                // rank / ranks (one GPU each), reference src/global_vars.h:38
+extern int gpuDevice;                                        // CUDA device of this rank
+extern uint64_t pidShardWidth;                               // multi-rank: rank r keeps the particle IDs [r * width, (r+1) * width) (last rank: and above)
 extern std::vector<std::vector<Halo>> locHalos;             // [2][nHalos]
 extern std::vector<TupleSoA> locTuples;                     // [2]
 extern std::vector<std::vector<MergerTree>> locMTrees;      // [2]

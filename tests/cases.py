@@ -101,12 +101,15 @@ def _evolve(rng, state, halos, limbo, step, multi, p_merge, p_sub, p_vanish, mea
 def _catalogue(rng, halos, number, z_index, id_mode):
     H = len(halos)
     lists_p, lists_t = [], []
+    subs = {}                       # host index -> its subhalos, in list order
+    for s in halos:
+        if s["sub_of"] is not None:
+            subs.setdefault(s["sub_of"], []).append(s)
     for k, h in enumerate(halos):
         p, t = [h["parts"]], [h["types"]]
-        for s in halos:
-            if s["sub_of"] == k:
-                p.append(s["parts"])
-                t.append(s["types"])
+        for s in subs.get(k, ()):
+            p.append(s["parts"])
+            t.append(s["types"])
         lists_p.append(np.concatenate(p))
         lists_t.append(np.concatenate(t))
     perm = rng.permutation(H)

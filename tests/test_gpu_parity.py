@@ -184,3 +184,32 @@ def test_csr_upload_rebuilds_the_halo_index(eng, nptypes):
     bad = grouped[0][1].copy(); bad[3] = bad[4] + 1
     with pytest.raises(mb.MetroError):
         eng.upload(0, prm, grouped[0][0], halo_offset=bad)
+
+
+@pytest.mark.gpu
+def test_csr32_upload_equals_the_u64_upload(eng):
+    """metro_catalogue_upload_csr32 (IDs as 32-bit offsets from a base, widened on the device chunk by chunk) must leave exactly the
+    catalogue the 64-bit CSR upload leaves - also across several upload chunks and with a large base - and match identically."""
+    prm = mb.make_params(nptypes=2, max_orphan_steps=4)
+    spec = mb.SynthSpec(seed=9, n_halos=700, n_tuples=120_001, pid_bits=20, shard=0, n_shards=1)
+    base = np.uint64(7_000_000_000_000)
+    grouped = []
+    for s in range(2):
+        c = mb.synth_pair_host(prm, spec, s)
+        order = np.argsort(c.halo, kind="stable")
+        off = np.zeros(c.n_halos + 1, np.int64)
+        np.cumsum(np.bincount(c.halo, minlength=c.n_halos), out=off[1:])
+        grouped.append((mb.HostCatalogue(c.halo_id, c.npart, c.n_orphan_steps, c.is_token, c.pid[order] + base, c.halo[order], None), off))
+    lo = min(int(g.pid.min()) for g, _ in grouped)
+    for slot, (g, off) in enumerate(grouped):
+        p32 = (g.pid - np.uint64(lo)).astype(np.uint32)
+        eng.upload(slot, prm, mb.HostCatalogue(g.halo_id, g.npart, g.n_orphan_steps, g.is_token, None, None, None), halo_offset=off, pid32=p32, pid_base=lo)
+        back = eng.fetch_catalogue(slot)
+        np.testing.assert_array_equal(back.pid, g.pid)
+        np.testing.assert_array_equal(back.halo, g.halo)
+    res32 = eng.find_progenitors_and_clean(prm)
+    oprm = binding.Params(2, prm.min_part_cmp, prm.min_part_halo, prm.fac_orphan_steps, prm.max_orphan_steps, prm.flavour)
+    compare_result_with_oracle(res32, binding.match_pair(oprm, to_oracle_catalogue(grouped[0][0]), to_oracle_catalogue(grouped[1][0])))
+    with pytest.raises(mb.MetroError):
+        eng.upload(0, prm, mb.HostCatalogue(grouped[0][0].halo_id, grouped[0][0].npart, None, None, None, None, None), halo_offset=grouped[0][1],
+                   pid32=np.zeros(grouped[0][0].n_tuples, np.uint32), pid_base=(1 << 64) - 5)

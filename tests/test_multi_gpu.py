@@ -32,3 +32,23 @@ def test_sharded_match_equals_oracle(world, nptypes, front_end):
            "--master-port", str(29700 + world + nptypes), os.path.join(ROOT, "tests", "multi_gpu_worker.py"), str(nptypes)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_host_program_ranks_concatenate_to_the_single_gpu_file(tmp_path, world):
+    """`MetroCPP-b200 --ranks K cfg` (one process per GPU, every rank reads all files and keeps its particle-ID range, per-rank
+    .mtree files like the reference's, src/IOSettings.cpp:1086): the rank files concatenated in rank order are byte-identical to the
+    reference's single-task file, on the 20-snapshot token chain."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from tests import golden_io
+    from tests.test_host_program import BIN, write_case
+    snaps, params, mtree = golden_io.load("fullbox_chain20")
+    cfg, out = write_case(str(tmp_path), snaps, params, "gather", fullbox_names=True)
+    r = subprocess.run([BIN, "--ranks", str(world), cfg], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, METRO_PART_MIN_N="1000"))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    for number, text in mtree["gather"].items():
+        got = "".join(open(os.path.join(out, f"test_{number:03d}.{rank}.mtree")).read() for rank in range(world))
+        assert got == text, f"snapshot {number}"
