@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="tuples per snapshot of the CPU sample (about 20 s of reference CPU time incl. its file ingest)")
     ap.add_argument("--ref-sample", type=int, default=400_000)
+    ap.add_argument("--ref-ids", type=int, default=10_000_000, help="bound IDs per snapshot of the pair the multi-rank reference arm matches per step")
     return ap.parse_args()
 
 
@@ -124,10 +125,10 @@ def ncu_traffic():
 
 
 def pick_pid_bits(tuples_total_one_snapshot: int) -> int:
-    # ranks ~ tuples/1.15; the generator needs 2 x ranks <= 2^bits, bits even
+    # ranks ~ tuples/1.15; the generator needs 2 x ranks <= 2^bits: the smallest ID range in which about half of the particles are
+    # bound (BASELINE.json configs: dense IDs 1..2^30 for 5e8 bound IDs, 1..2^33 for 4e9)
     need = 2 * int(tuples_total_one_snapshot / 1.10) + 16
-    b = max(8, need.bit_length())
-    return b + (b & 1)
+    return max(8, need.bit_length())
 
 
 # --------------------------------------------------------------------------------------------
@@ -163,7 +164,7 @@ def ref_binary():
     return p if os.path.isfile(p) and os.access(p, os.X_OK) else None
 
 
-def prepare_ref_run(work, snaps):
+def prepare_ref_run(work, snaps, chunks=0):
     """Lay out one reference run.  The snapshot lists the reference normally obtains from
     scripts/find_*.sh are pre-seeded in tmp/output_*.tmp (it reuses them when present,
     reference src/IOSettings.cpp:253-262), so nothing under /root/reference is needed."""
@@ -173,7 +174,13 @@ def prepare_ref_run(work, snaps):
         os.makedirs(d, exist_ok=True)
     ss = sorted(snaps, key=lambda s: s.number)
     for s in ss:
-        ahf_io.write_snapshot(inp, s, with_types=False)
+        if chunks:
+            # full-box layout: one file pair per spatial sub-volume (x slab); task r reads chunks [r * nChunks/totTask, ...)
+            from oracle import synth_np
+            for c, part in enumerate(synth_np.split_slabs(s, chunks)):
+                ahf_io.write_snapshot(inp, part, chunk=c, with_types=False)
+        else:
+            ahf_io.write_snapshot(inp, s, with_types=False)
     with open(os.path.join(metro, "tmp", "output_n.tmp"), "w") as f:
         f.write(f"{len(ss)}\n")
     with open(os.path.join(metro, "tmp", "output_id.tmp"), "w") as f:
@@ -187,8 +194,16 @@ def prepare_ref_run(work, snaps):
     with open(os.path.join(metro, "data", "pk_planck.dat"), "w") as f:
         f.write("".join(f"{1e-4 * 2 ** i:.8g} {100.0 + i:.6g}\n" for i in range(11)))
     cfg = os.path.join(work, "config.cfg")
-    run_ref.write_config(cfg, metro=metro, inp=inp, out=out, n_snaps=len(ss), fullbox=False,
-                         params=dict(minPartHalo=30, minPartCmp=10, facOrphanSteps=15, maxOrphanSteps=None))
+    if chunks:
+        run_ref.write_config(cfg, metro=metro, inp=inp, out=out, n_snaps=len(ss), fullbox=True,
+                             params=dict(minPartHalo=100, minPartCmp=10, facOrphanSteps=100, maxOrphanSteps=15))      # config/fullbox_*.cfg
+        with open(cfg) as f:
+            text = f.read().replace("nChunks = 1", f"nChunks = {chunks}")
+        with open(cfg, "w") as f:
+            f.write(text)
+    else:
+        run_ref.write_config(cfg, metro=metro, inp=inp, out=out, n_snaps=len(ss), fullbox=False,
+                             params=dict(minPartHalo=30, minPartCmp=10, facOrphanSteps=15, maxOrphanSteps=None))
     return cfg
 
 
@@ -240,11 +255,72 @@ def cpu_baseline(sample_tuples):
 
 
 # --------------------------------------------------------------------------------------------
+def mp_ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "MetroCPP_gather_mp")
+    return p if os.path.isfile(p) and os.access(p, os.X_OK) else None
+
+
+def parse_mp_times(stdout):
+    """Rank 0's phase timers of one pair (reference src/main.cpp:178-283): buffer exchange, FindProgenitors forwards and
+    backwards (each ends in an MPI_Barrier, so rank 0's time is the slowest rank's), gather of the trees to rank 0."""
+    pats = {"exchange": r"Buffer exchanged in ([0-9.eE+-]+)s", "forward": r"forwards\.\.\.done in ([0-9.eE+-]+)s",
+            "backward": r"backwards\.\.\.done in ([0-9.eE+-]+)s", "gather": r"Merger Trees gathered in ([0-9.eE+-]+)s"}
+    out = {}
+    for k, pat in pats.items():
+        m = re.search(pat, stdout)
+        if not m:
+            raise RuntimeError(f"could not parse the reference's '{k}' timer:\n" + stdout[-2000:])
+        out[k] = float(m.group(1))
+    return out
+
+
 def run_reference_arm(args, rank):
+    """The reference's own CPU implementation on the host cores.  Preferred form: its REAL multi-rank full-box path - the unmodified
+    sources built with -DGATHER_TREES against the multi-process MPI shim (oracle/mpi_shim_mp), one rank per core, chunked AHF input
+    written from a numpy generator (oracle/synth_np.py; the product library is not involved).  Fallback when that binary is absent:
+    one single-rank ZOOM process per core, or the C restatement."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     cores = max(1, min(cores, 32))
+    if mp_ref_binary():
+        from oracle import mpirun_shim, synth_np
+        ids_per_snap = args.ref_ids
+        snaps = synth_np.synth_pair(1000, max(50, ids_per_snap // 500), ids_per_snap)
+        ids = sum(s.n_tuples for s in snaps)
+        work = tempfile.mkdtemp(prefix="metro_refmp_")
+        rates, phases = [], []
+        try:
+            cfg = prepare_ref_run(work, snaps, chunks=cores)
+            for step in range(args.warmup + args.steps):
+                for f in os.listdir(os.path.join(work, "output")):
+                    os.remove(os.path.join(work, "output", f))
+                t0 = time.perf_counter()
+                res = mpirun_shim.run(cores, [mp_ref_binary(), cfg], cwd=work, timeout=1800)
+                if any(r.returncode != 0 for r in res):
+                    raise RuntimeError("the multi-rank reference failed:\n" + res[0].stdout[-2000:])
+                ph = parse_mp_times(res[0].stdout)
+                if step >= args.warmup:
+                    rates.append((ids / sum(ph.values()), time.perf_counter() - t0))
+                    phases.append(ph)
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        value = statistics.mean(r for r, _ in rates)
+        ms = statistics.mean(t for _, t in rates) * 1e3
+        mean_ph = {k: statistics.mean(p[k] for p in phases) for k in phases[0]}
+        sample = (f"the reference's multi-rank full-box build (GATHER_TREES, unmodified sources, multi-process MPI shim), {cores} ranks = {cores} host cores, "
+                  f"{cores} chunk files per snapshot (x slabs), synthetic full-box pair of {ids_per_snap} bound IDs per snapshot from a numpy generator; "
+                  f"rate = (N_A+N_B) / (buffer exchange + FindProgenitors forwards + backwards + tree gather) on rank 0's timers "
+                  f"(its barriers make them the slowest rank's); file reading and .mtree writing are outside, as in the GPU arm")
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic",
+                "config": {"workload": "synthetic 1024^3 full-box snapshot pair (bounded CPU sample of it)", "sample_ids_per_step": ids,
+                           "reference_phase_seconds": mean_ph, "ranks": cores},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
     works, cfgs, ids = [], [], 0
     kind = "reference" if ref_binary() else "port"
     sample_sets = []
@@ -275,7 +351,7 @@ def run_reference_arm(args, rank):
             shutil.rmtree(w, ignore_errors=True)
     value = statistics.mean(r for r, _ in rates)
     ms = statistics.mean(t for _, t in rates) * 1e3
-    sample = (f"{cores} concurrent single-rank instances (no MPI runtime on the box), each a synthetic pair of "
+    sample = (f"{cores} concurrent single-rank instances (multi-rank binary not built), each a synthetic pair of "
               f"{args.ref_sample} bound IDs per snapshot; rate = sum over instances of (N_A+N_B)/(fwd+bwd seconds)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

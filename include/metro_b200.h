@@ -197,7 +197,7 @@ typedef struct {
 	uint64_t seed;
 	int64_t n_halos;        /* halos of the later catalogue                                   */
 	int64_t n_tuples;       /* target tuples of the later catalogue (approximate)             */
-	int32_t pid_bits;       /* even; particle IDs are a Feistel permutation over 2^pid_bits   */
+	int32_t pid_bits;       /* particle IDs are a (cycle-walking) Feistel permutation over 2^pid_bits */
 	int32_t shard, n_shards;/* keep only pids whose top bits fall in this shard (pid range)   */
 } metro_synth_spec;
 /* Generates BOTH catalogues of a pair directly in HBM and installs them in slots 0 and 1. */

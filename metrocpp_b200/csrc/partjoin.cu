@@ -214,6 +214,7 @@ struct HitPlan {
 	u32 slack;                  // fixed part of a region's capacity
 };
 #define HIT_MAX_PARTS 1024
+#define BD_DIRECT_RB 13          // residual pid bits of a bucket for which pass C's direct-address table is 32 KB
 #define HIT_EMPTY 0xFFFFFFFFu
 
 // catalogue-0 tuples per hit partition when pass A does not read the catalogue (its buckets are resident):
@@ -968,6 +969,9 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	int tb = 0;
 	const i64 nmax = std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
 	while ((nmax >> tb) > 3900 && tb < 20) tb++;                    // final buckets of 2-4 k keys per catalogue
+	// dense IDs: up to two more bucket bits if that leaves BD_DIRECT_RB residual pid bits, the width at which pass C runs its
+	// direct-address table at two CTAs per SM (catalogues in which fewer than half of the particle IDs are bound)
+	if (L.pid_bits - tb > BD_DIRECT_RB && L.pid_bits - tb <= BD_DIRECT_RB + 2 && L.pid_bits - BD_DIRECT_RB <= 20) tb = L.pid_bits - BD_DIRECT_RB;
 	tb = std::min(tb + finer, 20);
 	PartPlan P;
 	P.b1 = getenv("METRO_B1") ? atoi(getenv("METRO_B1")) : (tb > 18 ? tb - 9 : (tb + 1) / 2);

@@ -61,7 +61,7 @@ static uint64_t gcd_u64(uint64_t a, uint64_t b) { while (b) { uint64_t r = a % b
 static int build_table(const metro_synth_spec *spec, int nptypes, HostTable &T, char *err, size_t errlen)
 {
 	const int64_t H = spec->n_halos;
-	if (H < 1 || spec->n_tuples < H || spec->pid_bits < 8 || spec->pid_bits > 62 || (spec->pid_bits & 1) || spec->n_shards < 1 ||
+	if (H < 1 || spec->n_tuples < H || spec->pid_bits < 8 || spec->pid_bits > 62 || spec->n_shards < 1 ||
 	    spec->shard < 0 || spec->shard >= spec->n_shards || (spec->n_shards & (spec->n_shards - 1))) {
 		snprintf(err, errlen, "bad synth spec");
 		return METRO_ERR_INVALID;

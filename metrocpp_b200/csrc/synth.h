@@ -52,8 +52,8 @@ SYN_HD uint64_t syn_hash(uint64_t seed, uint64_t stream, uint64_t a, uint64_t b)
 	return syn_mix(syn_mix(syn_mix(seed ^ (stream * 0xD6E8FEB86659FD93ull)) ^ a) ^ (b * 0xC2B2AE3D27D4EB4Full));
 }
 
-// balanced 4-round Feistel network over 2k = bits
-SYN_HD uint64_t syn_feistel(uint64_t x, uint64_t seed, int bits)
+// balanced 4-round Feistel network over an even number of bits
+SYN_HD uint64_t syn_feistel_even(uint64_t x, uint64_t seed, int bits)
 {
 	const int k = bits / 2;
 	const uint64_t m = (1ull << k) - 1ull;
@@ -65,7 +65,7 @@ SYN_HD uint64_t syn_feistel(uint64_t x, uint64_t seed, int bits)
 	}
 	return (L << k) | R;
 }
-SYN_HD uint64_t syn_feistel_inv(uint64_t y, uint64_t seed, int bits)
+SYN_HD uint64_t syn_feistel_even_inv(uint64_t y, uint64_t seed, int bits)
 {
 	const int k = bits / 2;
 	const uint64_t m = (1ull << k) - 1ull;
@@ -77,6 +77,20 @@ SYN_HD uint64_t syn_feistel_inv(uint64_t y, uint64_t seed, int bits)
 		L = t ^ f; R = Rp;
 	}
 	return (L << k) | R;
+}
+// permutation of [0, 2^bits): an odd width walks the cycle of the (bits + 1)-bit network until it is back inside the domain
+// (two steps on average; the restriction of a permutation to a subset by cycle walking is a permutation of the subset)
+SYN_HD uint64_t syn_feistel(uint64_t x, uint64_t seed, int bits)
+{
+	if ((bits & 1) == 0) return syn_feistel_even(x, seed, bits);
+	do { x = syn_feistel_even(x, seed, bits + 1); } while (x >> bits);
+	return x;
+}
+SYN_HD uint64_t syn_feistel_inv(uint64_t y, uint64_t seed, int bits)
+{
+	if ((bits & 1) == 0) return syn_feistel_even_inv(y, seed, bits);
+	do { y = syn_feistel_even_inv(y, seed, bits + 1); } while (y >> bits);
+	return y;
 }
 
 SYN_HD int64_t syn_find_halo(const SynthTable &t, uint64_t rank)

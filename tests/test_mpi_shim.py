@@ -1,0 +1,59 @@
+"""The multi-process MPI shim (oracle/mpi_shim_mp + oracle/mpirun_shim.py): the UNMODIFIED reference, full-box build, run as K ranks on
+chunked AHF input must find the same trees as its single-rank run (committed golden text) - with nGrid = 4 every halo lies within the
+one-cell buffer of every task, so the multi-rank decomposition loses nothing here; rank 0 gathers the trees task by task, so their
+ORDER in the file follows the chunks, the content is identical - and must agree with the C oracle on a synthetic full-box pair from
+the numpy generator.  This is the CPU baseline of bench.py --impl reference."""
+import os
+import shutil
+import tempfile
+
+import pytest
+
+import bench
+from oracle import ahf_io, binding, mpirun_shim, synth_np
+from tests import golden_io
+
+BIN = bench.mp_ref_binary()
+pytestmark = pytest.mark.skipif(BIN is None, reason="oracle/_ref/MetroCPP_gather_mp not built (needs /root/reference: make -C oracle ref)")
+
+
+def trees(text):
+    """.mtree text -> {main halo ID: (npart, orphan flag, progenitor rows in file order)}"""
+    out = {t.main_id: (t.main_npart, t.orphan, t.progs) for t in ahf_io.parse_mtree(text)}
+    assert len(out) == len(ahf_io.parse_mtree(text))
+    return out
+
+
+def run_ranks(snaps, ranks):
+    work = tempfile.mkdtemp(prefix="metro_shim_test_")
+    try:
+        cfg = bench.prepare_ref_run(work, snaps, chunks=ranks)
+        res = mpirun_shim.run(ranks, [BIN, cfg], cwd=work, timeout=600)
+        assert all(r.returncode == 0 for r in res), res[0].stdout[-2000:]
+        out = {}
+        for fn in os.listdir(os.path.join(work, "output")):
+            if fn.endswith(".mtree"):
+                out[int(fn[len("test_"):len("test_") + 3])] = open(os.path.join(work, "output", fn)).read()
+        return out, res[0].stdout
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+@pytest.mark.parametrize("ranks", [1, 2, 4])
+def test_multi_rank_reference_reproduces_its_single_rank_trees(ranks):
+    snaps, params, mtree = golden_io.load("fullbox_chain20")
+    assert params == dict(minPartHalo=100, minPartCmp=10, facOrphanSteps=100, maxOrphanSteps=15)       # what prepare_ref_run writes for chunked runs
+    got, _ = run_ranks(snaps[-5:], ranks)
+    assert len(got) == 4
+    for number, text in got.items():
+        if ranks == 1:
+            assert text == mtree["gather"][number], f"snapshot {number}"
+        assert trees(text) == trees(mtree["gather"][number]), f"ranks={ranks} snapshot {number}"
+
+
+def test_multi_rank_reference_on_the_numpy_pair_equals_oracle():
+    snaps = synth_np.synth_pair(77, 400, 200_000)
+    got, stdout = run_ranks(snaps, 4)
+    bench.parse_mp_times(stdout)                             # the four phase timers the reference arm reads are all there
+    exp = binding.run_chain(snaps, dict(minPartHalo=100, minPartCmp=10, facOrphanSteps=100, maxOrphanSteps=15), flavour="gather")
+    assert {k: trees(v) for k, v in got.items()} == {k: trees(v) for k, v in exp.items()}
