@@ -51,6 +51,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=4_000_000, help="tuples per snapshot of the CPU sample (about 20 s of reference CPU time incl. its file ingest)")
+    ap.add_argument("--workload", default="pair", choices=["pair", "chain20", "lgf54"],
+                    help="pair: the headline 1024^3 pair (default).  chain20 / lgf54: BASELINE.json configs[4] / [3] - whole snapshot chains of distinct "
+                         "synthetic catalogues through upload -> match -> fetch -> shift, one GPU")
+    ap.add_argument("--chain-scale", type=float, default=1.0, help="scale factor on the halo and tuple counts of a chain workload")
     ap.add_argument("--ref-sample", type=int, default=400_000)
     ap.add_argument("--ref-ids", type=int, default=10_000_000, help="bound IDs per snapshot of the pair the multi-rank reference arm matches per step")
     return ap.parse_args()
@@ -164,7 +168,7 @@ def ref_binary():
     return p if os.path.isfile(p) and os.access(p, os.X_OK) else None
 
 
-def prepare_ref_run(work, snaps, chunks=0):
+def prepare_ref_run(work, snaps, chunks=0, ngrid=24):
     """Lay out one reference run.  The snapshot lists the reference normally obtains from
     scripts/find_*.sh are pre-seeded in tmp/output_*.tmp (it reuses them when present,
     reference src/IOSettings.cpp:253-262), so nothing under /root/reference is needed."""
@@ -175,7 +179,7 @@ def prepare_ref_run(work, snaps, chunks=0):
     ss = sorted(snaps, key=lambda s: s.number)
     for s in ss:
         if chunks:
-            # full-box layout: one file pair per spatial sub-volume (x slab); task r reads chunks [r * nChunks/totTask, ...)
+            # full-box layout: one file pair per spatial sub-volume (compact block); task r reads chunks [r * nChunks/totTask, ...)
             from oracle import synth_np
             for c, part in enumerate(synth_np.split_slabs(s, chunks)):
                 ahf_io.write_snapshot(inp, part, chunk=c, with_types=False)
@@ -198,7 +202,7 @@ def prepare_ref_run(work, snaps, chunks=0):
         run_ref.write_config(cfg, metro=metro, inp=inp, out=out, n_snaps=len(ss), fullbox=True,
                              params=dict(minPartHalo=100, minPartCmp=10, facOrphanSteps=100, maxOrphanSteps=15))      # config/fullbox_*.cfg
         with open(cfg) as f:
-            text = f.read().replace("nChunks = 1", f"nChunks = {chunks}")
+            text = f.read().replace("nChunks = 1", f"nChunks = {chunks}").replace("nGrid = 4", f"nGrid = {ngrid}")       # config/fullbox_17_11.cfg:41,66: nGrid = 24
         with open(cfg, "w") as f:
             f.write(text)
     else:
@@ -309,7 +313,7 @@ def run_reference_arm(args, rank):
         ms = statistics.mean(t for _, t in rates) * 1e3
         mean_ph = {k: statistics.mean(p[k] for p in phases) for k in phases[0]}
         sample = (f"the reference's multi-rank full-box build (GATHER_TREES, unmodified sources, multi-process MPI shim), {cores} ranks = {cores} host cores, "
-                  f"{cores} chunk files per snapshot (x slabs), synthetic full-box pair of {ids_per_snap} bound IDs per snapshot from a numpy generator; "
+                  f"{cores} chunk files per snapshot (compact sub-volumes, nGrid = 24 as config/fullbox_17_11.cfg), synthetic full-box pair of {ids_per_snap} bound IDs per snapshot from a numpy generator; "
                   f"rate = (N_A+N_B) / (buffer exchange + FindProgenitors forwards + backwards + tree gather) on rank 0's timers "
                   f"(its barriers make them the slowest rank's); file reading and .mtree writing are outside, as in the GPU arm")
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -604,9 +608,29 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
     import metrocpp_b200 as mb
     stream = torch.cuda.current_stream(dev)
     cats = []
+    keep_pinned = []
+    # the results land in a pinned arena (re-used every step)
+    arena = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    arena_pos = [0]
+
+    def pinned_alloc(shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        lo = (arena_pos[0] + 63) & ~63
+        if lo + n > arena.numel():
+            return np.zeros(shape, dtype)
+        arena_pos[0] = lo + n
+        return arena.numpy()[lo:lo + n].view(dtype).reshape(shape)
     for slot in range(2):
         H, N = eng.catalogue_sizes(slot)
         halos = eng.fetch_catalogue(slot, tuples=False)
+        # the halo table in pinned memory too (metro_catalogue: "host pointers, pinned preferred")
+        for name in ("halo_id", "npart", "n_orphan_steps", "is_token"):
+            a = getattr(halos, name)
+            t = torch.empty(a.shape, dtype={"uint64": torch.int64, "int32": torch.int32, "uint8": torch.uint8}[a.dtype.name], pin_memory=True)
+            v = t.numpy().view(a.dtype)
+            v[...] = a
+            setattr(halos, name, v)
+            keep_pinned.append(t)
         pid = torch.empty(N, dtype=torch.int64, pin_memory=True)
         halo = torch.empty(N, dtype=torch.int32, pin_memory=True)
         rc = eng.lib.metro_catalogue_fetch_tuples(eng.h, slot, pid.data_ptr(), halo.data_ptr(), None)
@@ -642,7 +666,8 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
             else:
                 eng.upload(slot, prm, hc, halo_offset=off.numpy())
         info = eng.match_pair(prm)
-        res = eng.fetch_result(info, raw=False)
+        arena_pos[0] = 0
+        res = eng.fetch_result(info, raw=False, alloc=pinned_alloc)
         d2h = res.tree_main.nbytes + res.tree_orphan.nbytes + res.tree_off.nbytes + res.clean_prog.nbytes + \
             res.clean_ncommon.nbytes + res.token_halo.nbytes
         return d2h, info
@@ -720,6 +745,110 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
                     " -> metro_match_pair -> metro_result_fetch (clean trees)"}
 
 
+CHAIN_WORKLOADS = {
+    # BASELINE.json configs[4]: full-box 20-snapshot chain with token / orphan tracking (config/fullbox_*.cfg settings, GATHER_TREES
+    # flavour); sizes from SURVEY.md section 8d
+    "chain20": dict(n_snaps=20, halos=100_000, tuples=50_000_000, multi=False, nptypes=2, flavour="gather",
+                    params=dict(min_part_cmp=10, min_part_halo=100, fac_orphan_steps=100, max_orphan_steps=15),
+                    text="full-box 20-snapshot chain, ~1e5 halos / ~5e7 bound IDs per snapshot, tokens on (minPartHalo=100 facOrphanSteps=100 maxOrphanSteps=15)"),
+    # BASELINE.json configs[3]: multi-species Local Group zoom, 54 snapshots (config/lgf_gas.cfg settings, ZOOM build with NPTYPES=6)
+    "lgf54": dict(n_snaps=54, halos=20_000, tuples=10_000_000, multi=True, nptypes=6, flavour="zoom",
+                  params=dict(min_part_cmp=10, min_part_halo=30, fac_orphan_steps=50, max_orphan_steps=0),
+                  text="multi-species (gas / DM / stars, NPTYPES=6) zoom chain of 54 snapshots, ~2e4 halos / ~1e7 bound IDs per snapshot, 2 % of the gas turns "
+                       "into stars per step (minPartHalo=30 facOrphanSteps=50, maxOrphanSteps unset)"),
+}
+
+
+def run_chain_workload(args):
+    """A whole chain of DISTINCT snapshots through the calls the reference's main loop makes per older snapshot (src/main.cpp:154-308):
+    upload of the next catalogue from pinned host memory (CSR, u32 ID offsets when they fit), match (resident buckets of the previous
+    pair where the layout allows), fetch of the clean trees, shift.  Per-step device and end-to-end times; one JSON line."""
+    import numpy as np
+    import torch
+    import metrocpp_b200 as mb
+    from oracle import synth_np                              # (the numpy input generator; no checker involved in this leg)
+    w = CHAIN_WORKLOADS[args.workload]
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    halos, tuples = max(50, int(w["halos"] * args.chain_scale)), max(5000, int(w["tuples"] * args.chain_scale))
+    t_gen = time.perf_counter()
+    snaps = synth_np.synth_chain(20261020, w["n_snaps"], halos, tuples, multi_species=w["multi"])
+    t_gen = time.perf_counter() - t_gen
+    prm = mb.make_params(nptypes=w["nptypes"], flavour=mb.FLAVOUR_GATHER if w["flavour"] == "gather" else mb.FLAVOUR_ZOOM_DUP, **w["params"])
+    base = int(min(int(s.pid.min()) for s in snaps))
+    narrow = max(int(s.pid.max()) for s in snaps) - base < (1 << 32)
+    cats = []
+    for s in sorted(snaps, key=lambda x: -x.number):         # latest first
+        H = s.n_halos
+        npart = np.zeros((H, w["nptypes"]), np.int32)
+        npart[:, 1] = s.npart                                 # what IOSettings::ReadHalos fills (src/IOSettings.cpp:961-989)
+        ids = torch.empty(s.n_tuples, dtype=torch.int32 if narrow else torch.int64, pin_memory=True)
+        if narrow:
+            np.subtract(s.pid, np.uint64(base), out=ids.numpy().view(np.uint32), casting="unsafe")
+        else:
+            ids.numpy().view(np.uint64)[:] = s.pid
+        typ = None
+        if w["multi"]:
+            typ = torch.empty(s.n_tuples, dtype=torch.uint8, pin_memory=True)
+            typ.numpy()[:] = s.ptype
+        off = torch.empty(H + 1, dtype=torch.int64, pin_memory=True)
+        off.numpy()[:] = s.offsets
+        cats.append((mb.HostCatalogue(np.ascontiguousarray(s.halo_id, np.uint64), npart, np.zeros(H, np.int32), np.zeros(H, np.uint8), None, None,
+                                      None if typ is None else typ.numpy()), ids, off, s.n_tuples))
+    del snaps
+    eng = mb.MetroEngine(0)
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+
+    def upload(slot, c):
+        hc, ids, off, _ = c
+        if narrow:
+            eng.upload(slot, prm, hc, halo_offset=off.numpy(), pid32=ids.numpy().view(np.uint32), pid_base=base)
+        else:
+            hc2 = mb.HostCatalogue(hc.halo_id, hc.npart, hc.n_orphan_steps, hc.is_token, ids.numpy().view(np.uint64), None, hc.type)
+            eng.upload(slot, prm, hc2, halo_offset=off.numpy())
+
+    def run_chain():
+        steps = []
+        upload(0, cats[0])
+        for k in range(1, len(cats)):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            upload(1, cats[k])
+            info = eng.match_pair(prm)
+            res = eng.fetch_result(info, raw=False)
+            tm = eng.timings()
+            eng.shift_halos_parts(prm)
+            torch.cuda.synchronize(dev)
+            steps.append({"wall_ms": (time.perf_counter() - t0) * 1e3, "device_ms": tm["total"], "path": tm["path"], "resident": tm["resident"],
+                          "ids": int(sum(info["n_tuples"])), "trees": int(info["n_trees"]), "tokens": int(info["n_tokens"]), "launches": tm["total_launches"],
+                          "passes_ms": [round(x, 3) for x in tm["sort_pass_ms"][:4]], "select_ms": round(tm["select"], 3),
+                          "h2d_bytes": cats[k][1].numel() * cats[k][1].element_size() + cats[k][2].numel() * 8 + (cats[k][3] if w["multi"] else 0)})
+        return steps
+    run_chain()                                              # warm-up: allocations, plans
+    sampler = ClockSampler(0)
+    sampler.start()
+    steps = run_chain()
+    clocks = sampler.stop()
+    ids = sum(s["ids"] for s in steps)
+    wall = sum(s["wall_ms"] for s in steps)
+    devms = sum(s["device_ms"] for s in steps)
+    line = {"metric": METRIC, "value": ids / (devms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": len(steps), "warmup": len(steps),
+            "ms_per_step": devms / len(steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w['text']}", "halos_latest": int(cats[0][0].n_halos), "bound_ids_latest": int(cats[0][3]),
+                       "snapshots": len(cats), "scale": args.chain_scale, "generator_seconds": round(t_gen, 1),
+                       "ids_over_the_bus": "u32 offsets from the smallest ID" if narrow else "u64",
+                       "l2": "every catalogue is a distinct snapshot; keys per pass exceed the L2 at full scale"},
+            "clocks": clocks, "gpu_launches": int(sum(s["launches"] for s in steps)),
+            "e2e": {"value": ids / (wall * 1e-3), "unit": UNIT, "ms_per_step": wall / len(steps), "h2d_bytes_per_step": int(statistics.mean(s["h2d_bytes"] for s in steps)),
+                    "d2h_bytes_per_step": None, "path": "per older snapshot: metro_catalogue_upload_csr[32] -> metro_match_pair -> metro_result_fetch -> metro_shift"},
+            "chain": {"resident_steps": int(sum(s["resident"] for s in steps)), "partition_path_steps": int(sum(s["path"] == 1 for s in steps)),
+                      "wall_ms_all": [round(s["wall_ms"], 2) for s in steps], "device_ms_all": [round(s["device_ms"], 3) for s in steps],
+                      "tokens_all": [s["tokens"] for s in steps], "first_steps": steps[:3], "last_step": steps[-1]}}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -727,6 +856,11 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.workload != "pair":
+        if world > 1:
+            raise SystemExit("the chain workloads run on one GPU")
+        run_chain_workload(args)
         return
     run_ours(args, rank, world, local_rank)
 

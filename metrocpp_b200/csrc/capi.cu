@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256) upload_chunk_kernel(const u32 *__restrict
 	}
 }
 
-#define UP_CHUNK (16ll << 20)   // tuples per upload chunk (128 MB of u64 IDs: 2-3 ms over PCIe 5)
+static const i64 UP_CHUNK = getenv("METRO_UP_CHUNK") ? std::max<i64>(1 << 16, atoll(getenv("METRO_UP_CHUNK"))) : (16ll << 20);   // tuples per upload chunk (128 MB of u64 IDs: 2-3 ms over PCIe 5)
 
 // Tuples host -> HBM.  The copy runs in chunks on the context's copy stream; every chunk is checked (and, for 32-bit ID offsets,
 // widened) on the compute stream while the next one is crossing the bus, so the upload costs the bus time and nothing else.

@@ -75,23 +75,38 @@ __global__ void __launch_bounds__(SC_THREADS) scan_lookback_kernel(const u32 *__
 	}
 	u32 tot;
 	u32 run = block_exclusive_scan(sum, s_warp, &tot);
-	if (threadIdx.x == 0) {
+	// look-back by the first warp: 32 predecessors per step, newest first; a lane whose tile has published nothing yet makes the
+	// warp re-read the window
+	if (threadIdx.x < 32) {
 		volatile u64 *vs = state;
+		const int lane = threadIdx.x;
 		u64 prefix = 0;
-		if (tile == 0) vs[0] = SC_INC | (u64) tot;
+		if (tile == 0) { if (lane == 0) vs[0] = SC_INC | (u64) tot; }
 		else {
-			vs[tile] = SC_AGG | (u64) tot;
+			if (lane == 0) { vs[tile] = SC_AGG | (u64) tot; }
 			__threadfence();
-			for (i64 t = (i64) tile - 1; t >= 0; t--) {
-				u64 w;
-				do { w = vs[t]; } while ((w >> 62) == 0);
-				prefix += w & SC_VAL;
-				if ((w >> 62) == 2) break;
+			i64 hi = (i64) tile - 1;                                     // newest tile not yet accounted for
+			while (hi >= 0) {
+				const i64 t = hi - lane;
+				u64 w = t >= 0 ? vs[t] : SC_INC;                       // before the array: an inclusive prefix of 0
+				const u32 ready = __ballot_sync(0xffffffffu, (w >> 62) != 0);
+				const u32 inc = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+				const int stop = inc ? __ffs(inc) - 1 : 31;              // newest lane holding an inclusive prefix (else: the whole window)
+				const u32 need = stop == 31 ? 0xffffffffu : ((2u << stop) - 1u);
+				if ((ready & need) != need) continue;                    // a tile this side of the stop has published nothing yet: re-read
+				u64 val = lane <= stop ? (w & SC_VAL) : 0;
+#pragma unroll
+				for (int off = 16; off > 0; off >>= 1) val += __shfl_xor_sync(0xffffffffu, val, off);
+				prefix += val;
+				if (inc) break;
+				hi -= 32;
 			}
-			vs[tile] = SC_INC | (prefix + (u64) tot);
+			if (lane == 0) vs[tile] = SC_INC | (prefix + (u64) tot);
 		}
-		s_prefix = prefix;
-		if (total && (i64) (tile + 1) * SC_TILE >= n) *total = prefix + (u64) tot;
+		if (lane == 0) {
+			s_prefix = prefix;
+			if (total && (i64) (tile + 1) * SC_TILE >= n) *total = prefix + (u64) tot;
+		}
 	}
 	__syncthreads();
 	run += (u32) s_prefix;

@@ -168,24 +168,27 @@ class MetroEngine:
         return {k: (list(getattr(info, k)) if k in ("n_halos", "raw_count", "n_tuples") else getattr(info, k))
                 for k, _ in _lib.ResultInfo._fields_}
 
-    def fetch_result(self, info: dict, raw: bool = True) -> MatchResult:
+    def fetch_result(self, info: dict, raw: bool = True, alloc=None) -> MatchResult:
+        """alloc(shape, dtype) -> ndarray: where the results land (default: fresh numpy arrays; pass an allocator of pinned memory to
+        receive them at full PCIe rate)."""
         T = self.nptypes
         H = info["n_halos"]
         M = info["raw_count"]
+        new = alloc or (lambda shape, dtype: np.zeros(shape, dtype))
         ra = _lib.ResultArrays()
-        raw_off = [np.zeros(H[d] + 1, np.int64) for d in range(2)]
-        raw_prog = [np.zeros(M[d], np.int32) for d in range(2)]
-        raw_nc = [np.zeros((M[d], T), np.int32) for d in range(2)]
-        raw_merit = [np.zeros(M[d], np.uint32) for d in range(2)]
+        raw_off = [new(H[d] + 1 if raw else 0, np.int64) for d in range(2)]
+        raw_prog = [new(M[d] if raw else 0, np.int32) for d in range(2)]
+        raw_nc = [new((M[d] if raw else 0, T), np.int32) for d in range(2)]
+        raw_merit = [new(M[d] if raw else 0, np.uint32) for d in range(2)]
         if raw:
             for d in range(2):
                 ra.raw_off[d], ra.raw_prog[d] = _ptr(raw_off[d]), _ptr(raw_prog[d])
                 ra.raw_ncommon[d], ra.raw_merit[d] = _ptr(raw_nc[d]), _ptr(raw_merit[d])
         nt, cc, nk = info["n_trees"], info["clean_count"], info["n_tokens"]
-        tree_main, tree_orphan = np.zeros(nt, np.int32), np.zeros(nt, np.uint8)
-        tree_off = np.zeros(nt + 1, np.int64)
-        clean_prog, clean_nc = np.zeros(cc, np.int32), np.zeros((cc, T), np.int32)
-        token = np.zeros(nk, np.int32)
+        tree_main, tree_orphan = new(nt, np.int32), new(nt, np.uint8)
+        tree_off = new(nt + 1, np.int64)
+        clean_prog, clean_nc = new(cc, np.int32), new((cc, T), np.int32)
+        token = new(nk, np.int32)
         ra.tree_main, ra.tree_orphan, ra.tree_off = _ptr(tree_main), _ptr(tree_orphan), _ptr(tree_off)
         ra.clean_prog, ra.clean_ncommon, ra.token_halo = _ptr(clean_prog), _ptr(clean_nc), _ptr(token)
         self._check(self.lib.metro_result_fetch(self.h, C.byref(ra)))

@@ -24,10 +24,10 @@ def trees(text):
     return out
 
 
-def run_ranks(snaps, ranks):
+def run_ranks(snaps, ranks, ngrid=4):
     work = tempfile.mkdtemp(prefix="metro_shim_test_")
     try:
-        cfg = bench.prepare_ref_run(work, snaps, chunks=ranks)
+        cfg = bench.prepare_ref_run(work, snaps, chunks=ranks, ngrid=ngrid)
         res = mpirun_shim.run(ranks, [BIN, cfg], cwd=work, timeout=600)
         assert all(r.returncode == 0 for r in res), res[0].stdout[-2000:]
         out = {}
@@ -57,3 +57,10 @@ def test_multi_rank_reference_on_the_numpy_pair_equals_oracle():
     bench.parse_mp_times(stdout)                             # the four phase timers the reference arm reads are all there
     exp = binding.run_chain(snaps, dict(minPartHalo=100, minPartCmp=10, facOrphanSteps=100, maxOrphanSteps=15), flavour="gather")
     assert {k: trees(v) for k, v in got.items()} == {k: trees(v) for k, v in exp.items()}
+    # With the grid of the reference's full-box configs (nGrid = 24: 4 Mpc/h cells, one-cell buffer) a task only sees the earlier halos
+    # around its own volume: progenitors further away are LOST, decomposition-dependent (reference README:37).
+    # The main progenitor sits where its descendant sits, so it survives; that is what the timing baseline relies on.
+    got24, _ = run_ranks(snaps, 4, ngrid=24)
+    g, e = trees(got24[2]), trees(exp[2])
+    same_main = sum(1 for k in e if k in g and g[k][2][:1] == e[k][2][:1])
+    assert same_main >= 0.95 * len(e), (same_main, len(e))
