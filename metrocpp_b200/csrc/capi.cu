@@ -427,74 +427,87 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	//  * LSD radix sort by pid + run-length join (any size; also the fallback when a bucket overflows)
 	i64 R = 0, hits = 0;
 	int sort_launches = 0;
-	static const bool force_lsd = getenv("METRO_FORCE_LSD") && atoi(getenv("METRO_FORCE_LSD"));
-	static const bool no_resident = getenv("METRO_NO_RESIDENT") && atoi(getenv("METRO_NO_RESIDENT"));
-	ctx->timings.path = 0;
-	ctx->timings.resident = 0;
-	bool part = false;
 	KeyLayout Lp = L;                                       // layout the partition path runs with
-	if (!force_lsd && !wide) {
-		// chain step: the buckets of catalogue 0 are resident if its tuples are the ones they were built from and
-		// this pair fits the layout and plan they were built with
-		PartResident &Rs = ctx->resident;
-		const i64 nmax = std::max(c0.n_tuples, c1.n_tuples);
-		bool reuse0 = !no_resident && Rs.cat0 && Rs.gen == c0.gen && c0.n_tuples > 0 && Rs.L.type_bits == type_bits && halo_bits <= Rs.L.halo_bits &&
-			      pid_base >= Rs.pid_base && nmax <= Rs.nmax_cap &&
-			      ceil_log2_u64(std::max(c0.max_pid, c1.max_pid) - Rs.pid_base) <= Rs.L.pid_bits;
-		static const bool dbg = getenv("METRO_DEBUG") != nullptr;
-		if (dbg && Rs.cat0 && !reuse0)
-			fprintf(stderr, "[metro] resident buckets not reused: gen %d type %d halo %d (%d<=%d) base %d (%llu>=%llu) nmax %d (%lld<=%lld) pidbits %d\n",
-				Rs.gen == c0.gen, Rs.L.type_bits == type_bits, halo_bits <= Rs.L.halo_bits, halo_bits, Rs.L.halo_bits, pid_base >= Rs.pid_base,
-				(unsigned long long) pid_base, (unsigned long long) Rs.pid_base, nmax <= Rs.nmax_cap, (long long) nmax, (long long) Rs.nmax_cap,
-				ceil_log2_u64(std::max(c0.max_pid, c1.max_pid) - Rs.pid_base) <= Rs.L.pid_bits);
-		// attempt 0: resident plan; 1: fresh plan; 2, 3: fresh plan with 2x / 4x finer buckets after a per-bucket overflow
-		// (table or hit staging: more memberships per particle than the default bucket size provides for)
-		int finer = ctx->part_finer;
-		for (int attempt = reuse0 ? 0 : 1; attempt < 4 && !part; attempt++) {
-			PartPlan PP;
-			bool fell_back = false;
-			u32 mask = 0;
-			if (attempt == 0) {
-				PP = Rs.P; Lp = Rs.L; ctx->pid_base = Rs.pid_base;
-			} else {
-				// a fresh plan; one spare halo bit so that the token halos of the next shifts still fit the layout
-				const int hb = (halo_bits + 1 + 2 * type_bits <= 31 && pid_bits + 2 + halo_bits + type_bits <= 64) ? halo_bits + 1 : halo_bits;
-				Lp = make_key_layout(pid_bits, hb, type_bits);
-				ctx->pid_base = pid_base;
-				i64 ncap = 0;
-				if (!partition_join_plan(ctx, Lp, N, &PP, &ncap, finer)) break;
-				Rs.nmax_cap = ncap;
+	auto front_end = [&]() -> int {
+		static const bool force_lsd = getenv("METRO_FORCE_LSD") && atoi(getenv("METRO_FORCE_LSD"));
+		static const bool no_resident = getenv("METRO_NO_RESIDENT") && atoi(getenv("METRO_NO_RESIDENT"));
+		ctx->timings.path = 0;
+		ctx->timings.resident = 0;
+		bool part = false;
+		if (!force_lsd && !wide) {
+			// chain step: the buckets of catalogue 0 are resident if its tuples are the ones they were built from and
+			// this pair fits the layout and plan they were built with
+			PartResident &Rs = ctx->resident;
+			const i64 nmax = std::max(c0.n_tuples, c1.n_tuples);
+			bool reuse0 = !no_resident && Rs.cat0 && Rs.gen == c0.gen && c0.n_tuples > 0 && Rs.L.type_bits == type_bits && halo_bits <= Rs.L.halo_bits &&
+				      pid_base >= Rs.pid_base && nmax <= Rs.nmax_cap &&
+				      ceil_log2_u64(std::max(c0.max_pid, c1.max_pid) - Rs.pid_base) <= Rs.L.pid_bits;
+			static const bool dbg = getenv("METRO_DEBUG") != nullptr;
+			if (dbg && Rs.cat0 && !reuse0)
+				fprintf(stderr, "[metro] resident buckets not reused: gen %d type %d halo %d (%d<=%d) base %d (%llu>=%llu) nmax %d (%lld<=%lld) pidbits %d\n",
+					Rs.gen == c0.gen, Rs.L.type_bits == type_bits, halo_bits <= Rs.L.halo_bits, halo_bits, Rs.L.halo_bits, pid_base >= Rs.pid_base,
+					(unsigned long long) pid_base, (unsigned long long) Rs.pid_base, nmax <= Rs.nmax_cap, (long long) nmax, (long long) Rs.nmax_cap,
+					ceil_log2_u64(std::max(c0.max_pid, c1.max_pid) - Rs.pid_base) <= Rs.L.pid_bits);
+			// attempt 0: resident plan; 1: fresh plan; 2, 3: fresh plan with 2x / 4x finer buckets after a per-bucket overflow
+			// (table or hit staging: more memberships per particle than the default bucket size provides for)
+			int finer = ctx->part_finer;
+			for (int attempt = reuse0 ? 0 : 1; attempt < 4 && !part; attempt++) {
+				PartPlan PP;
+				bool fell_back = false;
+				u32 mask = 0;
+				if (attempt == 0) {
+					PP = Rs.P; Lp = Rs.L; ctx->pid_base = Rs.pid_base;
+				} else {
+					// a fresh plan; one spare halo bit so that the token halos of the next shifts still fit the layout
+					const int hb = (halo_bits + 1 + 2 * type_bits <= 31 && pid_bits + 2 + halo_bits + type_bits <= 64) ? halo_bits + 1 : halo_bits;
+					Lp = make_key_layout(pid_bits, hb, type_bits);
+					ctx->pid_base = pid_base;
+					i64 ncap = 0;
+					if (!partition_join_plan(ctx, Lp, N, &PP, &ncap, finer)) break;
+					Rs.nmax_cap = ncap;
+				}
+				CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+				if ((rc = stage_partition_join(ctx, Lp, PP, halo_bits, attempt == 0, &R, &hits, &fell_back, &mask, finer > 0))) return rc;
+				if (!fell_back) { part = true; ctx->timings.path = 1; ctx->timings.resident = attempt == 0; sort_launches = 4; if (attempt >= 1) ctx->part_finer = finer; }
+				else if (attempt >= 1) {
+					if ((mask & ~6u) != 0 || finer >= 2) break;      // region / record overflows are not cured by finer buckets: LSD path
+					finer++;
+				}
 			}
-			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-			if ((rc = stage_partition_join(ctx, Lp, PP, halo_bits, attempt == 0, &R, &hits, &fell_back, &mask, finer > 0))) return rc;
-			if (!fell_back) { part = true; ctx->timings.path = 1; ctx->timings.resident = attempt == 0; sort_launches = 4; if (attempt >= 1) ctx->part_finer = finer; }
-			else if (attempt >= 1) {
-				if ((mask & ~6u) != 0 || finer >= 2) break;      // region / record overflows are not cured by finer buckets: LSD path
-				finer++;
-			}
+			if (!part) ctx->pid_base = pid_base;
 		}
-		if (!part) ctx->pid_base = pid_base;
-	}
-	// the wide-key and LSD front ends overwrite keys_a / keys_b: whatever buckets were resident there are gone
-	if (wide || !part) { ctx->resident.cat0 = false; ctx->resident.cat1 = false; }
-	if (wide) {
-		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-		if ((rc = stage_wide_join(ctx, L, pid_bits, &R, &hits, &sort_launches))) return rc;
-		ctx->timings.path = 2;
-	} else if (!part) {
-		if ((rc = dev_reserve(ctx, ctx->keys_a, (size_t) N * 8 + 16))) return rc;
-		if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) N * 8 + 16))) return rc;
-		if ((rc = sort_workspace_reserve(ctx, ctx->sortws, N))) return rc;
-		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-		if ((rc = stage_pack_hist(ctx, L, plan))) return rc;
-		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
-		u64 *sorted = nullptr;
-		if ((rc = sort_scatter_passes(ctx, st, ctx->sortws, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), nullptr, nullptr, N, plan, &sorted, nullptr,
-					      ctx->ev_pass, &sort_launches))) return rc;
-		ctx->launches += sort_launches;
-		sort_launches = N > 0 ? plan.n_pass : 0;
-		CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
-		if ((rc = stage_join_count(ctx, L, sorted, N, &R, &hits))) return rc;
+		// the wide-key and LSD front ends overwrite keys_a / keys_b: whatever buckets were resident there are gone
+		if (wide || !part) { ctx->resident.cat0 = false; ctx->resident.cat1 = false; }
+		if (wide) {
+			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+			if ((rc = stage_wide_join(ctx, L, pid_bits, &R, &hits, &sort_launches))) return rc;
+			ctx->timings.path = 2;
+		} else if (!part) {
+			if ((rc = dev_reserve(ctx, ctx->keys_a, (size_t) N * 8 + 16))) return rc;
+			if ((rc = dev_reserve(ctx, ctx->keys_b, (size_t) N * 8 + 16))) return rc;
+			if ((rc = sort_workspace_reserve(ctx, ctx->sortws, N))) return rc;
+			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
+			if ((rc = stage_pack_hist(ctx, L, plan))) return rc;
+			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
+			u64 *sorted = nullptr;
+			if ((rc = sort_scatter_passes(ctx, st, ctx->sortws, ctx->keys_a.as<u64>(), ctx->keys_b.as<u64>(), nullptr, nullptr, N, plan, &sorted, nullptr,
+						      ctx->ev_pass, &sort_launches))) return rc;
+			ctx->launches += sort_launches;
+			sort_launches = N > 0 ? plan.n_pass : 0;
+			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
+			if ((rc = stage_join_count(ctx, L, sorted, N, &R, &hits))) return rc;
+		}
+		return METRO_OK;
+	};
+	// Every rank must take the same exit: a rank that failed here (allocation, a table overflow on its shard) would otherwise
+	// strand its peers in the collectives of the exchange.  The ranks agree on the worst status first.
+	rc = front_end();
+	{
+		const int agreed = comm_agree_status(ctx, rc);
+		if (agreed != METRO_OK) {
+			if (rc == METRO_OK) metro_set_error(ctx, "another rank failed in the join stage (status %d)", agreed);
+			return rc != METRO_OK ? rc : agreed;
+		}
 	}
 	res.info.n_hits = hits;
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[3], st));

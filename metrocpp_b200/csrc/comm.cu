@@ -53,6 +53,20 @@ int comm_allreduce_sum_u64(metro_ctx *ctx, u64 *buf, i64 n)
 	return METRO_OK;
 }
 
+// max of a status code over the ranks (no-op on one GPU); one small all-reduce + one stream synchronisation
+int comm_agree_status(metro_ctx *ctx, int rc)
+{
+	if (ctx->world <= 1) return rc;
+	cudaStream_t st = ctx->stream;
+	u64 *d = ctx->counters.as<u64>() + 62;
+	ctx->h_counters[62] = (u64) (rc < 0 ? 0 : rc);
+	if (cudaMemcpyAsync(d, ctx->h_counters + 62, sizeof(u64), cudaMemcpyHostToDevice, st) != cudaSuccess) return rc ? rc : METRO_ERR_CUDA;
+	if (ncclAllReduce(d, d, 1, ncclUint64, ncclMax, comm_of(ctx), st) != ncclSuccess) return rc ? rc : METRO_ERR_COMM;
+	if (cudaMemcpyAsync(ctx->h_counters + 62, d, sizeof(u64), cudaMemcpyDeviceToHost, st) != cudaSuccess) return rc ? rc : METRO_ERR_CUDA;
+	if (cudaStreamSynchronize(st) != cudaSuccess) return rc ? rc : METRO_ERR_CUDA;
+	return (int) ctx->h_counters[62];
+}
+
 void comm_destroy(metro_ctx *ctx)
 {
 	if (ctx->comm) ncclCommDestroy(comm_of(ctx));

@@ -136,6 +136,7 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &L, co
 // comm.cu (NCCL; no-ops on a single GPU)
 int comm_allreduce_max_i32(metro_ctx *ctx, i32 *buf, i64 n);
 int comm_allreduce_sum_u64(metro_ctx *ctx, u64 *buf, i64 n);
+int comm_agree_status(metro_ctx *ctx, int rc);
 int comm_exchange_records(metro_ctx *ctx, int halo_bits, int type_bits, const u64 *rec_key, const u32 *rec_cnt, i64 R,
 			  const u64 **recA_key, const u32 **recA_cnt, i64 *RA, const u64 **recB_key, const u32 **recB_cnt, i64 *RB);
 void comm_owned_range(const metro_ctx *ctx, i64 H, i64 *lo, i64 *hi);

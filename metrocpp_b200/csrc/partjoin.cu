@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(BD_THREADS, 2) bucket_join_direct_kernel(const
 #define HR_MAX_UNITS (2 * HIT_MAX_PARTS)   // sum of ceil(c_d / (3 mean)) <= nbh + nbh / 3
 #define HR_MAX_SUB_LOG 4                   // a partition holds up to 2^4 sub-ranges of 2048 halos: 32 M catalogue-0 halos per GPU
 
-__global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__restrict__ hit_cnt, u32 nbh, uint4 *__restrict__ units, u32 *n_units)
+__global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__restrict__ hit_cnt, u32 nbh, u32 min_units, uint4 *__restrict__ units, u32 *n_units)
 {
 	__shared__ u64 s_warp[32];
 	const u32 d = threadIdx.x;
@@ -766,6 +766,7 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__r
 	block_excl_scan_u64(c, s_warp, &total);
 	u64 slice_max = 3 * (total / nbh) + 1;                          // only partitions well above the mean are split
 	if (slice_max < 65536) slice_max = 65536;
+	(void) min_units;
 	const u64 nsl = c ? (c + slice_max - 1) / slice_max : 0;
 	// longest units first (blocks are scheduled in index order: a heavy unit started last would be the tail):
 	// rank of this partition by its per-unit size, ties by index
@@ -1008,10 +1009,14 @@ static HitPlan make_hit_plan(int rec_halo_bits, int type_bits, i64 H0)
 	hp.rec_a_shift = rec_halo_bits + 2 * type_bits;
 	// 2048 halos x 4 ways x 8 B = 64 KB: two pass-D blocks per SM (METRO_LOG_HP=12: 4096 halos per range from the start, one
 	// 1024-thread block per SM - half as many ranges for pass C to partition the hits into)
-	static const int base_log = getenv("METRO_LOG_HP") && atoi(getenv("METRO_LOG_HP")) == 12 ? 12 : 11;
+	static const int env_log = getenv("METRO_LOG_HP") && atoi(getenv("METRO_LOG_HP")) == 12 ? 12 : 11;
+	auto parts = [&](int lg) { return (u64) div_up<i64>(std::max<i64>(H0, 1), 1ll << lg); };
+	// catalogues with few halos (a zoom: 2e4 halos would be 10 ranges of 2048): narrower ranges, down to 16 halos, until there are at
+	// least as many ranges as pass D has block slots - every SM gets work and no pair is counted in two places
+	int base_log = env_log;
+	while (base_log > 4 && parts(base_log) < 2 * METRO_NUM_SMS_B200) base_log--;
 	hp.ways = 4; hp.log_hs = base_log;
 	hp.log_hp = base_log;
-	auto parts = [&](int lg) { return (u64) div_up<i64>(std::max<i64>(H0, 1), 1ll << lg); };
 	while (parts(hp.log_hp) > HIT_MAX_PARTS && hp.log_hp < 11 + HR_MAX_SUB_LOG) hp.log_hp++;
 	if (hp.log_hp > hp.log_hs) hp.log_hs = 12;                       // sub-range mode: 4096 halos x 4 ways = 128 KB, one 1024-thread block per SM
 	hp.nbh = (u32) parts(hp.log_hp);
@@ -1074,6 +1079,7 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	// 2 hits per catalogue-0 tuple + the per-range slack; the tuple counts are sampled (every HIST_SAMPLE-th tile, scaled) by up to two
 	// streams (resident part: hit_hist_kernel; the rest: pass A), each over-estimating by up to HIST_SAMPLE tiles
 	const u64 hits_cap = 2ull * ((u64) c0.n_tuples + 2ull * HIST_SAMPLE * PT_TILE) + (u64) (hp.slack + 2) * hp.nbh;
+	const u32 min_units = 0;
 	const u64 rec_cap = 16ull * (u64) (c0.n_halos + c1.n_halos) + (1ull << 20);
 	int rc;
 	// keys_a: level-1 regions, dead after pass B and reused for the hit regions
@@ -1162,7 +1168,7 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	}
 	CUDA_TRY(ctx, cudaEventRecord(ctx->ev[10], st));
 	// pass D
-	hit_units_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(hit_cnt, hp.nbh, units, n_units);
+	hit_units_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(hit_cnt, hp.nbh, min_units, units, n_units);
 	CUDA_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
 	if (hp.log_hp == hp.log_hs && hp.log_hs == 12) rc = launch_reduce<4, false, 2 * HR_THREADS>(ctx, hp, ctx->keys_a.as<u64>(), hit_base, hit_cnt, units, n_units, ctx->scratch[0].as<u64>(), ctx->scratch[1].as<u32>(), rec_cap, ovf);

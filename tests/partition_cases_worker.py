@@ -76,10 +76,17 @@ def main():
     extra = (np.arange(3 * n, dtype=np.uint64) + np.uint64(1 << 23))
     run_case(eng, "unbalanced", catalogue(later, 10**6, rng), catalogue(earlier + split(rng, extra, 1500), 2 * 10**6, rng), prm, expect_path=1)
 
-    # 4. deep nesting: every particle of the earlier catalogue is a member of 3 halos (more than 2 hits per
-    #    catalogue-0 tuple over whole ranges => hit regions overflow => LSD fallback, same answer)
+    # 4. nesting: every particle of the earlier catalogue is a member of 3 halos (3 hits per catalogue-0 tuple): stays on the
+    #    partition path (the hit ranges of a small catalogue carry enough slack), same answer
     nest = earlier + [np.concatenate(earlier[i::40]) for i in range(40)] + [np.concatenate(earlier[i::7]) for i in range(7)]
-    run_case(eng, "triple_membership", catalogue(later, 10**6, rng), catalogue(nest, 2 * 10**6, rng), prm, expect_path=0)
+    run_case(eng, "triple_membership", catalogue(later, 10**6, rng), catalogue(nest, 2 * 10**6, rng), prm, expect_path=1)
+
+    # 4b. deep nesting: every particle is a member of 21 earlier halos (21 hits per catalogue-0 tuple over whole ranges, 20 chain
+    #     nodes per table slot => chain nodes / hit regions overflow => finer buckets do not cure it => LSD fallback, same answer)
+    deep = list(earlier)
+    for k in (3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71, 73):
+        deep += [np.concatenate(earlier[i::k]) for i in range(k)]
+    run_case(eng, "deep_nesting", catalogue(later, 10**6, rng), catalogue(deep, 2 * 10**6, rng), prm, expect_path=0)
 
     # 5. one particle ID listed in 200 earlier halos and 50 later halos (10^4 hits from one ID: the bucket table's
     #    last-resort list overflows => LSD fallback)

@@ -132,3 +132,58 @@ def test_ingest_grammar_edge_cases(tmp_path):
         for kv in parsed:
             assert int(kv["halos"]) == 4 and int(kv["tuples"]) == len(exp) and int(kv["tuple_ck"]) == exp_ck, (threads, kv)
         assert "2 particle lines belong to halo IDs that are not in the halo catalogue" in err
+
+
+# ---- .mtree reader compatibility ---------------------------------------------------------------------------------
+def reader_rules(text):
+    """What the reference's own post-processing reader makes of a .mtree file (python/mtreelib/read_mtree.py:98-145): a line of 4
+    fields opens a tree (descendant ID, its particles, number of progenitors, orphan flag), the FIRST following line of 3 fields is its
+    main progenitor (particles, ID, common particles); everything else is skipped.  -> {descID: (progID, common, descNPart, descNProg)}"""
+    out, n_prog_line, desc = {}, 0, None
+    for line in text.splitlines():
+        f = line.split()
+        if len(f) == 4:
+            desc, n_prog_line = (f[0], int(f[1]), int(f[2])), 0
+        if len(f) == 3:
+            n_prog_line += 1
+            if n_prog_line == 1:
+                out[desc[0]] = (f[1], int(f[2]), desc[1], desc[2])
+    return out
+
+
+@pytest.mark.skipif(not os.path.isfile("/root/reference/python/mtreelib/read_mtree.py"), reason="needs the reference's python/ tree")
+@pytest.mark.parametrize("name", ["chain6_tokens", "fullbox_chain20"])
+def test_reference_python_reader_parses_our_mtree_layout(tmp_path, name):
+    """The reference's reader, imported from /root/reference/python, on the .mtree text of the fixtures (byte-identical to what
+    IOSettings::WriteTree of the host program writes, see the GPU test below): same main-branch dictionary as the restated rules,
+    and the file names are the ones ReadSettings.gen_file_list builds (baseFile + '%03d.' + '%d.' + suffFile)."""
+    import sys
+    sys.path.insert(0, "/root/reference/python")
+    try:
+        from mtreelib import read_mtree
+    finally:
+        sys.path.pop(0)
+    snaps, params, mtree = golden_io.load(name)
+    flavour = "gather" if "gather" in mtree else sorted(mtree)[0]
+    numbers = sorted(mtree[flavour], reverse=True)
+    for number in numbers:
+        path = tmp_path / f"test_{number:03d}.0.mtree"
+        path.write_text(mtree[flavour][number])
+        got = read_mtree.read_metrocpp_tree(str(path))
+        exp = reader_rules(mtree[flavour][number])
+        assert set(got) == set(exp) and len(exp) > 0
+        for k, dp in got.items():
+            assert (dp.progID, int(dp.progNPart), int(dp.descNPart), int(dp.descNProg)) == exp[k]
+    settings = read_mtree.ReadSettings(str(tmp_path / "test_"), "mtree", 1, numbers[0], len(numbers))
+    assert [f[0] for f in settings.treeFiles] == [str(tmp_path / f"test_{n:03d}.0.mtree") for n in numbers]
+
+
+@pytest.mark.gpu
+def test_host_program_output_reads_like_the_reference_output(tmp_path):
+    snaps, params, mtree = golden_io.load("chain6_tokens")
+    cfg, out = write_case(str(tmp_path), snaps, params, "zoom")
+    r = subprocess.run([BIN, cfg], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    for number, text in mtree["zoom"].items():
+        got = open(os.path.join(out, f"test_{number:03d}.0.mtree")).read()       # the name the reference's reader looks for
+        assert reader_rules(got) == reader_rules(text) and len(reader_rules(got)) > 0
