@@ -366,6 +366,32 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: run this rank (and first-touch its pinned host buffers) on the NUMA node its GPU hangs off, so that the
+    8 ranks of a node do not all pull their host-to-device copies through one memory controller.  Best effort: returns the node or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # --------------------------------------------------------------------------------------------
 def sharded_parity_check(eng, rank, world, dist, dev):
     """N>1 only, before anything is timed: a small pair (1500 halos, 2.5e5 tuples per snapshot) sharded by particle-ID range over
@@ -439,6 +465,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
 
     H_glob, N_glob = args.halos * world, args.tuples * world
     pid_bits = args.pid_bits or pick_pid_bits(N_glob)
@@ -587,6 +614,8 @@ def run_ours(args, rank, world, local_rank):
         line["e2e"] = e2e
     if parity:
         line["parity_check"] = parity
+    if world > 1:
+        line["config"]["numa_node_rank0"] = numa_node
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -232,13 +232,36 @@ __global__ void __launch_bounds__(256) seg_sort_mid_kernel(const u64 *__restrict
 	}
 }
 
-// long segments: rank by counting (keys are distinct: the position breaks ties), one block per segment
+// long segments, one block per segment: up to 4096 entries by a bitonic network on (key, position) in shared memory; beyond that
+// (a halo with more than 4096 candidate records) rank by counting (keys are distinct: the position breaks ties), O(L^2)
+#define SEG_LONG_SMEM 4096
 __global__ void __launch_bounds__(256) seg_sort_long_kernel(const u64 *__restrict__ key, const u32 *__restrict__ segoff, const u32 *__restrict__ segcnt,
 							     const u32 *__restrict__ long_list, const u32 *__restrict__ n_lists, u32 *__restrict__ sidx)
 {
-	__shared__ u32 s_low[2048];
+	__shared__ u64 s_k[SEG_LONG_SMEM];
+	u32 *s_low = reinterpret_cast<u32 *>(s_k);                          // counting path: 2048 staged keys
 	for (u32 s = blockIdx.x; s < n_lists[1]; s += gridDim.x) {
 		const u32 a = long_list[s], L = segcnt[a], off = segoff[a];
+		if (L <= SEG_LONG_SMEM) {
+			u32 n = 64;
+			while (n < L) n <<= 1;
+			for (u32 i = threadIdx.x; i < n; i += 256) s_k[i] = i < L ? ((key[off + i] & 0xFFFFFFFFull) << 32) | i : ~0ull;
+			__syncthreads();
+			for (u32 size = 2; size <= n; size <<= 1) {
+				for (u32 stride = size >> 1; stride > 0; stride >>= 1) {
+					for (u32 t = threadIdx.x; t < n / 2; t += 256) {
+						const u32 lo = 2 * t - (t & (stride - 1)), hi = lo + stride;     // partner pair of thread t
+						const bool up = (lo & size) == 0;
+						const u64 x = s_k[lo], y = s_k[hi];
+						if ((x > y) == up) { s_k[lo] = y; s_k[hi] = x; }
+					}
+					__syncthreads();
+				}
+			}
+			for (u32 i = threadIdx.x; i < L; i += 256) sidx[off + i] = off + (u32) (s_k[i] & 0xFFFFFFFFull);
+			__syncthreads();
+			continue;
+		}
 		for (u32 i0 = 0; i0 < L; i0 += 256) {
 			const u32 i = i0 + threadIdx.x;
 			const u32 mine = i < L ? (u32) key[off + i] : 0u;
@@ -574,28 +597,38 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	const i64 KB_max = sharded ? RB : RA;                    // upper bound of the backward list
 	const u64 *cKB = sharded ? cnt + C_K_BWD : cnt + C_K_FWD;
 
+	// Sharded runs: every pair arrives once per pid shard, so the record lists are `world` times longer than the pair lists they
+	// merge into.  One small read-back of the kept-pair counts lets everything downstream be sized by the pairs, not the records
+	// (on one GPU the two are about equal and the stage stays free of host round trips).
+	i64 nA = RA, nB = KB_max;
+	if (sharded) TRY(merge_records(ctx, prm, hl, recB_key, recB_cnt, RB, rank0, true, H1, b_lo, b_hi, S + 64, cnt + C_P_BWD, cnt + C_K_BWD));
+	if (ctx->world > 1) {
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + C_P_FWD, cnt + C_P_FWD, 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+		CUDA_TRY(ctx, cudaStreamSynchronize(st));
+		nA = (i64) ctx->h_counters[C_K_FWD];
+		nB = (i64) ctx->h_counters[sharded ? C_K_BWD : C_K_FWD];
+	}
 	// 3. forward raw tree (locMTrees[0])
-	DirList fwd = {S[17].as<u32>(), S[18].as<u32>(), S[19].as<i32>(), S[21].as<i32>(), RA, cnt + C_K_FWD};
+	DirList fwd = {S[17].as<u32>(), S[18].as<u32>(), S[19].as<i32>(), S[21].as<i32>(), nA, cnt + C_K_FWD};
 	TRY(build_tree(ctx, fwd, H0, a_lo, a_hi, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), S + 40, S[22], S[23], S[24], res.raw_prog[0],
 		       res.raw_ncommon[0], res.raw_merit[0]));
 	// 4. backward raw tree (locMTrees[1]): the pairs ordered by (B, ID(A)), by-type counts of the 0 side
 	DirList bwd;
 	if (sharded) {
-		// the records routed to owner(B) are merged in backward order right away: no second sort
-		TRY(merge_records(ctx, prm, hl, recB_key, recB_cnt, RB, rank0, true, H1, b_lo, b_hi, S + 64, cnt + C_P_BWD, cnt + C_K_BWD));
-		bwd = {S[65].as<u32>(), S[64].as<u32>(), S[67].as<i32>(), S[68].as<i32>(), RB, cKB};
+		// the records routed to owner(B) were merged in backward order right away: no second sort
+		bwd = {S[65].as<u32>(), S[64].as<u32>(), S[67].as<i32>(), S[68].as<i32>(), nB, cKB};
 	} else {
-		RES(S[25], KB_max * 4); RES(S[26], KB_max * 4); RES(S[27], KB_max * T * 4); RES(S[28], KB_max * 4);
-		if (KB_max > 0) {
-			RES(S[40], KB_max * 4); RES(S[41], KB_max * 8); RES(S[42], KB_max * 4);
-			rank_of_kernel<<<GRID(KB_max), TPB, 0, st>>>(S[17].as<u32>(), rank0, KB_max, cKB, S[40].as<u32>()); LAUNCHED();
+		RES(S[25], nB * 4); RES(S[26], nB * 4); RES(S[27], nB * T * 4); RES(S[28], nB * 4);
+		if (nB > 0) {
+			RES(S[40], nB * 4); RES(S[41], nB * 8); RES(S[42], nB * 4);
+			rank_of_kernel<<<GRID(nB), TPB, 0, st>>>(S[17].as<u32>(), rank0, nB, cKB, S[40].as<u32>()); LAUNCHED();
 			u32 *perm = S[42].as<u32>();
-			TRY(group_by(ctx, S[18].as<u32>(), S[40].as<u32>(), KB_max, cKB, H1, b_lo, b_hi, S + 70, S[76], S[77], perm, S[41].as<u64>()));
-			gather_dir_kernel<<<GRID(KB_max), TPB, 0, st>>>(perm, cKB, T, S[18].as<u32>(), S[17].as<u32>(), S[20].as<i32>(), S[21].as<i32>(),
-									 S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>());
+			TRY(group_by(ctx, S[18].as<u32>(), S[40].as<u32>(), nB, cKB, H1, b_lo, b_hi, S + 70, S[76], S[77], perm, S[41].as<u64>()));
+			gather_dir_kernel<<<GRID(nB), TPB, 0, st>>>(perm, cKB, T, S[18].as<u32>(), S[17].as<u32>(), S[20].as<i32>(), S[21].as<i32>(),
+								     S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>());
 			LAUNCHED();
 		}
-		bwd = {S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>(), KB_max, cKB};
+		bwd = {S[25].as<u32>(), S[26].as<u32>(), S[27].as<i32>(), S[28].as<i32>(), nB, cKB};
 	}
 	TRY(build_tree(ctx, bwd, H1, b_lo, b_hi, T, c1.npart_tot.as<i32>(), c0.npart_tot.as<i32>(), S + 40, S[29], S[30], S[31], res.raw_prog[1],
 		       res.raw_ncommon[1], res.raw_merit[1]));
@@ -611,15 +644,15 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	best_desc_kernel<<<GRID(H1), TPB, 0, st>>>(S[30].as<u32>(), S[29].as<u32>(), res.raw_prog[1].as<i32>(), H1, S[32].as<i32>()); LAUNCHED();
 	// multi-GPU: the owner of each catalogue-1 halo knows its best descendant, everybody needs it
 	TRY(comm_allreduce_max_i32(ctx, S[32].as<i32>(), H1));
-	RES(S[33], RA * 4); RES(S[34], RA * 4); RES(S[35], (H0 + 1) * 4); RES(S[36], (H0 + 1) * 4);
+	RES(S[33], nA * 4); RES(S[34], nA * 4); RES(S[35], (H0 + 1) * 4); RES(S[36], (H0 + 1) * 4);
 	u32 *cntc = S[35].as<u32>(), *cstart = S[36].as<u32>();
 	CUDA_TRY(ctx, cudaMemsetAsync(cntc, 0, (size_t) (H0 + 1) * 4, st));
 	CUDA_TRY(ctx, cudaMemsetAsync(cnt + C_UNTRACKED, 0, sizeof(u64), st));
-	if (RA > 0) {
-		clean_flag_kernel<<<GRID(RA), TPB, 0, st>>>(S[24].as<u32>(), res.raw_prog[0].as<i32>(), RA, cnt + C_K_FWD, S[32].as<i32>(), c0.halo_id.as<u64>(),
+	if (nA > 0) {
+		clean_flag_kernel<<<GRID(nA), TPB, 0, st>>>(S[24].as<u32>(), res.raw_prog[0].as<i32>(), nA, cnt + C_K_FWD, S[32].as<i32>(), c0.halo_id.as<u64>(),
 							     S[33].as<u32>(), cntc);
 		LAUNCHED();
-		TRY(scan_exclusive_u32(ctx, st, S[33].as<u32>(), S[34].as<u32>(), RA, nullptr));
+		TRY(scan_exclusive_u32(ctx, st, S[33].as<u32>(), S[34].as<u32>(), nA, nullptr));
 	}
 	TRY(scan_exclusive_u32(ctx, st, cntc, cstart, H0 + 1, nullptr));
 	// orphan / token rule
@@ -645,11 +678,11 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	TRY(comm_allreduce_max_i32(ctx, reinterpret_cast<i32 *>(gtoken), H0));
 	TRY(scan_exclusive_u32(ctx, st, gtoken, kscan, H0 + 1, cnt + C_TOKENS));
 
-	// clean list grouped by A (kept entries in first-sort order, or the single token entry): C <= K + tokens <= RA + H0 entries
-	const i64 C_max = RA + H0;
+	// clean list grouped by A (kept entries in first-sort order, or the single token entry): C <= K + tokens of the owned halos
+	const i64 C_max = nA + (a_hi - a_lo);
 	RES(Q[3], C_max * 4); RES(Q[4], C_max * 4); RES(Q[5], C_max * T * 4); RES(Q[6], C_max * 4);
-	if (RA > 0) {
-		clean_fill_kernel<<<GRID(RA), TPB, 0, st>>>(S[33].as<u32>(), S[34].as<u32>(), cnt + C_K_FWD, T, S[24].as<u32>(), res.raw_prog[0].as<i32>(),
+	if (nA > 0) {
+		clean_fill_kernel<<<GRID(nA), TPB, 0, st>>>(S[33].as<u32>(), S[34].as<u32>(), cnt + C_K_FWD, T, S[24].as<u32>(), res.raw_prog[0].as<i32>(),
 							     res.raw_ncommon[0].as<i32>(), cstart, coff, Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(),
 							     Q[6].as<i32>());
 		LAUNCHED();

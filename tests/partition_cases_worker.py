@@ -114,6 +114,14 @@ def main():
     run_case(eng, "fragmented_giant", catalogue([giant] + mids + rest, 10**6, rng),
              catalogue(pieces + mid_pieces + [x[: int(0.9 * len(x))] for x in rest], 2 * 10**6, rng), prm)
 
+    # 6c. the same with 6000 earlier halos of 12 particles: more candidates in one tree than the shared-memory sort of the long-segment
+    #     kernel holds (4096): its counting path
+    giant2 = ids[:72_000]
+    pieces2 = np.array_split(giant2, 6000)
+    rest2 = split(rng, ids[72_000:], 500)
+    run_case(eng, "fragmented_giant_6000", catalogue([giant2] + rest2, 10**6, rng),
+             catalogue(pieces2 + [x[: int(0.9 * len(x))] for x in rest2], 2 * 10**6, rng), prm)
+
     # 7. multi-species, ZOOM flavour
     prm6 = mb.make_params(nptypes=6, max_orphan_steps=3, flavour=mb.FLAVOUR_ZOOM_DUP)
     spec = mb.SynthSpec(seed=11, n_halos=3000, n_tuples=600_000, pid_bits=22, shard=0, n_shards=1)
