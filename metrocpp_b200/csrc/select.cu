@@ -584,6 +584,19 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	u64 *cnt = ctx->counters.as<u64>();
 	HitLayout hl = {KL.halo_bits, KL.type_bits};
 
+	// METRO_PROF_SELECT=1: phase times of this stage on stderr (CUDA events; rank 0 only)
+	static const bool prof = getenv("METRO_PROF_SELECT") != nullptr;
+	static cudaEvent_t pev[16];
+	static bool pev_ok = false;
+	int n_mark = 0;
+	const char *mark_name[16];
+	auto MARK = [&](const char *name) {
+		if (!prof || ctx->rank != 0 || n_mark >= 16) return;
+		if (!pev_ok) { for (auto &e : pev) cudaEventCreate(&e); pev_ok = true; }
+		mark_name[n_mark] = name;
+		cudaEventRecord(pev[n_mark++], st);
+	};
+	MARK("start");
 	// halo-ID ranks (std::map iteration order of indexCommon is ascending halo ID, not file order)
 	TRY(id_ranks(ctx, c0, S + 40));
 	TRY(id_ranks(ctx, c1, S + 40));
@@ -593,6 +606,7 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	i64 b_lo = 0, b_hi = H1;                                  // catalogue-1 halos whose backward trees this rank builds
 	comm_owned_range(ctx, H1, &b_lo, &b_hi);
 	TRY(merge_records(ctx, prm, hl, recA_key, recA_cnt, RA, rank1, false, H0, a_lo, a_hi, S + 17, cnt + C_P_FWD, cnt + C_K_FWD));
+	MARK("merge forward records");
 	const bool sharded = recB_key != recA_key;
 	const i64 KB_max = sharded ? RB : RA;                    // upper bound of the backward list
 	const u64 *cKB = sharded ? cnt + C_K_BWD : cnt + C_K_FWD;
@@ -608,10 +622,12 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 		nA = (i64) ctx->h_counters[C_K_FWD];
 		nB = (i64) ctx->h_counters[sharded ? C_K_BWD : C_K_FWD];
 	}
+	MARK("merge backward records + sizes");
 	// 3. forward raw tree (locMTrees[0])
 	DirList fwd = {S[17].as<u32>(), S[18].as<u32>(), S[19].as<i32>(), S[21].as<i32>(), nA, cnt + C_K_FWD};
 	TRY(build_tree(ctx, fwd, H0, a_lo, a_hi, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), S + 40, S[22], S[23], S[24], res.raw_prog[0],
 		       res.raw_ncommon[0], res.raw_merit[0]));
+	MARK("forward tree");
 	// 4. backward raw tree (locMTrees[1]): the pairs ordered by (B, ID(A)), by-type counts of the 0 side
 	DirList bwd;
 	if (sharded) {
@@ -639,11 +655,13 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 		LAUNCHED();
 	}
 
+	MARK("backward tree");
 	// 5. CleanTrees: mutual-best filter
 	RES(S[32], (H1 + 1) * 4);
 	best_desc_kernel<<<GRID(H1), TPB, 0, st>>>(S[30].as<u32>(), S[29].as<u32>(), res.raw_prog[1].as<i32>(), H1, S[32].as<i32>()); LAUNCHED();
 	// multi-GPU: the owner of each catalogue-1 halo knows its best descendant, everybody needs it
 	TRY(comm_allreduce_max_i32(ctx, S[32].as<i32>(), H1));
+	MARK("best descendant + all-reduce");
 	RES(S[33], nA * 4); RES(S[34], nA * 4); RES(S[35], (H0 + 1) * 4); RES(S[36], (H0 + 1) * 4);
 	u32 *cntc = S[35].as<u32>(), *cstart = S[36].as<u32>();
 	CUDA_TRY(ctx, cudaMemsetAsync(cntc, 0, (size_t) (H0 + 1) * 4, st));
@@ -678,6 +696,7 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	TRY(comm_allreduce_max_i32(ctx, reinterpret_cast<i32 *>(gtoken), H0));
 	TRY(scan_exclusive_u32(ctx, st, gtoken, kscan, H0 + 1, cnt + C_TOKENS));
 
+	MARK("mutual best, orphan rule, token all-reduce");
 	// clean list grouped by A (kept entries in first-sort order, or the single token entry): C <= K + tokens of the owned halos
 	const i64 C_max = nA + (a_hi - a_lo);
 	RES(Q[3], C_max * 4); RES(Q[4], C_max * 4); RES(Q[5], C_max * T * 4); RES(Q[6], C_max * 4);
@@ -696,6 +715,7 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	DirList cl = {Q[3].as<u32>(), Q[4].as<u32>(), Q[5].as<i32>(), Q[6].as<i32>(), C_max, cnt + C_CLEAN};
 	TRY(build_tree(ctx, cl, H0, a_lo, a_hi, T, c0.npart_tot.as<i32>(), c1.npart_tot.as<i32>(), S + 40, Q[7], Q[8], Q[9], res.clean_prog,
 		       res.clean_ncommon, Q[10]));
+	MARK("clean list + second merit sort");
 	// trees and tokens: at most one per catalogue-0 halo
 	RES(res.tree_main, H0 * 4); RES(res.tree_orphan, H0); RES(res.tree_off, (H0 + 1) * 8); RES(res.token_halo, H0 * 4);
 	if (H0 > 0) {
@@ -705,9 +725,15 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 		token_emit_kernel<<<GRID(H0), TPB, 0, st>>>(gtoken, kscan, H0, res.token_halo.as<i32>()); LAUNCHED();
 	}
 	tree_off_end_kernel<<<1, 1, 0, st>>>(res.tree_off.as<i64>(), cnt + C_TREES, cnt + C_CLEAN); LAUNCHED();
+	MARK("emit");
 	// the one host round trip of the stage: sizes for the caller
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters, cnt, 40 * sizeof(u64), cudaMemcpyDeviceToHost, st));
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
+	if (n_mark > 1) {
+		fprintf(stderr, "[metro] select (RA %lld RB %lld nA %lld nB %lld H0 %lld):", (long long) RA, (long long) RB, (long long) nA, (long long) nB, (long long) H0);
+		for (int i = 1; i < n_mark; i++) { float ms = 0; cudaEventElapsedTime(&ms, pev[i - 1], pev[i]); fprintf(stderr, " %s %.3f ms;", mark_name[i], ms); }
+		fprintf(stderr, "\n");
+	}
 	const u64 *h = ctx->h_counters;
 	res.info.n_pairs = (i64) h[C_P_FWD];
 	res.info.raw_count[0] = (i64) h[C_K_FWD];

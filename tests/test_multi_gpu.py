@@ -52,3 +52,20 @@ def test_host_program_ranks_concatenate_to_the_single_gpu_file(tmp_path, world):
     for number, text in mtree["gather"].items():
         got = "".join(open(os.path.join(out, f"test_{number:03d}.{rank}.mtree")).read() for rank in range(world))
         assert got == text, f"snapshot {number}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2])
+def test_sharded_match_at_size_equals_oracle(world):
+    """1e6 halos / 1.2e8 tuples generated on the devices, one pid shard per GPU, through the sharded partition join; the concatenated
+    per-rank raw and clean trees and the tokens compared in full with the oracle on the unsharded data (tests/multi_gpu_at_size_worker.py)."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs 180 GB B200s")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29760 + world), os.path.join(ROOT, "tests", "multi_gpu_at_size_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT, env=dict(os.environ, METRO_DEBUG="1"))
+    assert r.returncode == 0 and "MULTI_GPU_AT_SIZE_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "partition join attempt overflowed" not in r.stderr, r.stderr[-2000:]
