@@ -73,6 +73,7 @@ void comm_destroy(metro_ctx *ctx)
 	ctx->comm = nullptr;
 	dev_free(ctx->xsend_key); dev_free(ctx->xsend_cnt); dev_free(ctx->xrecvA_key); dev_free(ctx->xrecvA_cnt);
 	dev_free(ctx->xrecvB_key); dev_free(ctx->xrecvB_cnt); dev_free(ctx->xcounts);
+	dev_free(ctx->xredA_key); dev_free(ctx->xredA_cnt); dev_free(ctx->xredB_key); dev_free(ctx->xredB_cnt);
 }
 
 // ---- routing ---------------------------------------------------------------------------------

@@ -112,6 +112,7 @@ struct metro_ctx {
 	i64 exchange_bytes = 0;         // bytes this rank sent to peers in the last all-to-all
 	bool exchange_timed = false;    // ev[11] .. ev[12] bracket the grouped send/recv of the last match
 	DevBuf xsend_key, xsend_cnt, xrecvA_key, xrecvA_cnt, xrecvB_key, xrecvB_cnt, xcounts;
+	DevBuf xredA_key, xredA_cnt, xredB_key, xredB_cnt;      // owner-side pre-reduced records (select.cu / partjoin.cu: stage_prereduce)
 };
 
 int dev_reserve(metro_ctx *ctx, DevBuf &b, size_t bytes);
@@ -128,6 +129,8 @@ int stage_pack_hist(metro_ctx *ctx, const KeyLayout &L, const SortPlan &plan);  
 bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap, int finer);     // partjoin.cu
 int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back,
 			 u32 *overflow_mask, bool finer_plan);
+int stage_prereduce(metro_ctx *ctx, const u64 *key, const u32 *cnt, i64 R, int halo_bits, int type_bits, bool swapped, i64 x_lo, i64 x_hi, DevBuf *W,
+		    DevBuf &okey, DevBuf &ocnt, u64 *d_total);                              // partjoin.cu (multi-GPU owner side)
 int stage_join_count(metro_ctx *ctx, const KeyLayout &L, const u64 *sorted, i64 n,
 		     i64 *n_records, i64 *n_hits);                                     // join.cu
 int stage_wide_join(metro_ctx *ctx, const KeyLayout &L, int pid_bits, i64 *n_records, i64 *n_hits, int *sort_launches);   // join.cu

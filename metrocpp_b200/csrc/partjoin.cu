@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(BD_THREADS, 2) bucket_join_direct_kernel(const
 // Work units: a partition, or a slice of a heavy one (a catalogue dominated by one halo); slices of
 // the same partition emit separate records for the same pair, which the selection stage sums.
 #define HR_THREADS 512
-#define HR_OVF 3072             // entries of the per-block hash table for pairs beyond a halo's WAYS slots (36 KB: table + queues + 64 KB of ways = 108 KB, two blocks per SM)
+#define HR_OVF 3072             // (== the constexpr OVF of the unweighted kernel) entries of the per-block hash table for pairs beyond a halo's WAYS slots (36 KB: table + queues + 64 KB of ways = 108 KB, two blocks per SM)
 #define HR_OVF_PROBES 32
 #define HR_MAX_UNITS (2 * HIT_MAX_PARTS)   // sum of ceil(c_d / slice_max) <= nbh + total / slice_max <= 2 nbh (slices of at least one mean)
 #define HR_MAX_SUB_LOG 4                   // a partition holds up to 2^4 sub-ranges of 2048 halos: 32 M catalogue-0 halos per GPU
@@ -792,8 +792,11 @@ __global__ void __launch_bounds__(HIT_MAX_PARTS) hit_units_kernel(const u32 *__r
 // would drag three quarters of the warp iterations through the slow code with one or two active lanes.  It is pushed on the warp's own
 // small queue (positions from a ballot, no atomics); whenever 32 are queued the warp runs the slow path once with all lanes busy.
 #define HR_QCAP 64              // queue entries per warp: < 32 before a push, <= 32 pushed
-template <int WAYS, bool SUB, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(const u64 *__restrict__ hits, const u64 *__restrict__ hit_base,
+// WEIGHTED (multi-GPU, owner side): the input is (record, partial count) pairs from all pid shards instead of single hits, every
+// record adds its count; HR_OVF_W overflow entries leave room for the weights on the queues.
+#define HR_OVF_W 2560
+template <int WAYS, bool SUB, int THREADS, bool WEIGHTED = false>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(const u64 *__restrict__ hits, const u32 *__restrict__ weights, const u64 *__restrict__ hit_base,
 								 const u32 *__restrict__ hit_cnt, const uint4 *__restrict__ units,
 								 const u32 *__restrict__ n_units, HitPlan hp, u64 *__restrict__ rec_key,
 								 u32 *__restrict__ rec_cnt, u64 rec_cap, u64 *counters, u32 *overflow)
@@ -802,12 +805,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(con
 	const u32 sub = SUB ? blockIdx.x & ((1u << sub_log) - 1u) : 0u;
 	if ((blockIdx.x >> sub_log) >= *n_units) return;
 	extern __shared__ __align__(16) unsigned char hsm[];
+	constexpr u32 OVF = WEIGHTED ? HR_OVF_W : 3072;                      // entries of the overflow table (== HR_OVF when unweighted)
 	const u32 HP = 1u << hp.log_hs;                                      // halos counted by this block
 	u32 *s_tag = reinterpret_cast<u32 *>(hsm);                           // [HP * WAYS]
 	u32 *s_count = s_tag + (size_t) HP * WAYS;                           // [HP * WAYS]
-	u64 *s_okey = reinterpret_cast<u64 *>(s_count + (size_t) HP * WAYS); // [HR_OVF] pairs whose halo ran out of ways: open addressing on the record
-	u32 *s_ocnt = reinterpret_cast<u32 *>(s_okey + HR_OVF);              // [HR_OVF]
-	u64 *s_queue = reinterpret_cast<u64 *>(s_ocnt + HR_OVF);             // [THREADS / 32][HR_QCAP]
+	u64 *s_okey = reinterpret_cast<u64 *>(s_count + (size_t) HP * WAYS); // [OVF] pairs whose halo ran out of ways: open addressing on the record
+	u32 *s_ocnt = reinterpret_cast<u32 *>(s_okey + OVF);              // [OVF]
+	u64 *s_queue = reinterpret_cast<u64 *>(s_ocnt + OVF);             // [THREADS / 32][HR_QCAP]
+	u32 *s_qw = reinterpret_cast<u32 *>(s_queue + (size_t) (THREADS / 32) * HR_QCAP);   // WEIGHTED: [THREADS / 32][HR_QCAP] counts of the queued records
 	__shared__ u32 s_warpsum[THREADS / 32];
 	__shared__ u64 s_base;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -818,7 +823,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(con
 	per = (per + 1) & ~1ull;
 	const u64 lo = (u64) u.y * per, hi = lo + per < cnt ? lo + per : cnt;
 	for (u32 i = tid; i < HP * WAYS; i += THREADS) { s_tag[i] = HIT_EMPTY; s_count[i] = 0; }
-	for (u32 i = tid; i < HR_OVF; i += THREADS) { s_okey[i] = ~0ull; s_ocnt[i] = 0; }
+	for (u32 i = tid; i < OVF; i += THREADS) { s_okey[i] = ~0ull; s_ocnt[i] = 0; }
 	__syncthreads();
 	const u64 *src = hits + hit_base[d];
 	const u32 tag_mask = (u32) ((1ull << hp.rec_a_shift) - 1ull);
@@ -826,10 +831,11 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(con
 	u32 spilled = 0;
 	bool ovf = false;           // record buffer full (cause 16)
 	u64 *queue = s_queue + (size_t) warp * HR_QCAP;
+	u32 *queue_w = s_qw + (size_t) warp * HR_QCAP;
 	u32 qn = 0;                 // entries on the warp's queue (same in all its lanes)
 	const u32 lt = lanemask_lt();
 	// slow path for one record per lane: claim a way, else the overflow table, else straight to the output
-	auto slow = [&](u64 rec) {
+	auto slow = [&](u64 rec, u32 wgt) {
 		const u32 a = (u32) (rec >> ash) & (HP - 1u);
 		const u32 tag = (u32) rec & tag_mask;
 		u32 *tg = s_tag + (size_t) a * WAYS;
@@ -843,8 +849,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(con
 			}
 			if (cur == tag) { w = x; break; }
 		}
-		if (w >= 0) { atomicAdd(s_count + (size_t) a * WAYS + w, 1u); return; }
-		u32 h = __umulhi((u32) ((rec * 0x9E3779B97F4A7C15ull) >> 32), (u32) HR_OVF);
+		if (w >= 0) { atomicAdd(s_count + (size_t) a * WAYS + w, wgt); return; }
+		u32 h = __umulhi((u32) ((rec * 0x9E3779B97F4A7C15ull) >> 32), (u32) OVF);
 		int probe = 0;
 		for (; probe < HR_OVF_PROBES; probe++) {
 			u64 cur = *reinterpret_cast<volatile u64 *>(s_okey + h);
@@ -852,13 +858,13 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(con
 				cur = atomicCAS((unsigned long long *) (s_okey + h), ~0ull, (unsigned long long) rec);
 				if (cur == ~0ull) cur = rec;
 			}
-			if (cur == rec) { atomicAdd(s_ocnt + h, 1u); break; }
-			h = h + 1 == HR_OVF ? 0u : h + 1;
+			if (cur == rec) { atomicAdd(s_ocnt + h, wgt); break; }
+			h = h + 1 == OVF ? 0u : h + 1;
 		}
 		if (probe == HR_OVF_PROBES) {
 			// last resort: a (record, 1) pair straight to the output
 			const u64 o = atomicAdd((unsigned long long *) &counters[2], 1ull);
-			if (o < rec_cap) { rec_key[o] = rec; rec_cnt[o] = 1u; }
+			if (o < rec_cap) { rec_key[o] = rec; rec_cnt[o] = wgt; }
 			else ovf = true;
 		}
 		spilled++;
@@ -868,20 +874,26 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(con
 	const u64 iters = (span + (u64) THREADS * UNR - 1) / ((u64) THREADS * UNR);           // same for all threads: whole warps stay in the loop
 	// software pipeline: the loads of batch it+1 are in flight while batch it is counted
 	u64 rn[UNR];
+	u32 wn[UNR];
+	const u32 *wsrc = WEIGHTED ? weights + hit_base[d] : nullptr;
 #pragma unroll
 	for (int q = 0; q < UNR; q++) {
 		const u64 j = lo + tid + (u64) q * THREADS;
 		rn[q] = j < hi ? ld_stream_u64(src + j) : ~0ull;
+		wn[q] = WEIGHTED && j < hi ? wsrc[j] : 1u;
 	}
 #pragma unroll 1
 	for (u64 it = 0; it < iters; it++) {
 		const u64 j1 = lo + (it + 1) * (u64) THREADS * UNR + tid;
 		u64 r[UNR];
+		u32 wq[UNR];
 #pragma unroll
 		for (int q = 0; q < UNR; q++) {
 			r[q] = rn[q];
+			wq[q] = wn[q];
 			const u64 j = j1 + (u64) q * THREADS;
 			rn[q] = j < hi ? ld_stream_u64(src + j) : ~0ull;
+			wn[q] = WEIGHTED && j < hi ? wsrc[j] : 1u;
 		}
 #pragma unroll
 		for (int q = 0; q < UNR; q++) {
@@ -898,29 +910,30 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(con
 				const uint2 t2 = *reinterpret_cast<const uint2 *>(s_tag + (size_t) a * 2);
 				w = t2.x == tag ? 0 : t2.y == tag ? 1 : -1;
 			}
-			if (valid && w >= 0) atomicAdd(s_count + (size_t) a * WAYS + w, 1u);
+			if (valid && w >= 0) atomicAdd(s_count + (size_t) a * WAYS + w, WEIGHTED ? wq[q] : 1u);
 			const bool pend = valid && w < 0;
 			const u32 bq = __ballot_sync(0xffffffffu, pend);
 			if (bq) {
-				if (pend) queue[qn + __popc(bq & lt)] = r[q];
+				if (pend) { queue[qn + __popc(bq & lt)] = r[q]; if (WEIGHTED) queue_w[qn + __popc(bq & lt)] = wq[q]; }
 				qn += __popc(bq);
 				if (qn >= 32) {
 					__syncwarp();
 					qn -= 32;
 					const u64 rec = queue[qn + lane];
+					const u32 rw = WEIGHTED ? queue_w[qn + lane] : 1u;
 					__syncwarp();
-					slow(rec);
+					slow(rec, rw);
 				}
 			}
 		}
 	}
 	__syncwarp();
-	if ((u32) lane < qn) slow(queue[lane]);
+	if ((u32) lane < qn) slow(queue[lane], WEIGHTED ? queue_w[lane] : 1u);
 	__syncthreads();
 	// emit the live ways + the overflow list
 	u32 live = 0;
 	for (u32 i = tid; i < HP * WAYS; i += THREADS) live += s_tag[i] != HIT_EMPTY;
-	for (u32 i = tid; i < HR_OVF; i += THREADS) live += s_okey[i] != ~0ull;
+	for (u32 i = tid; i < OVF; i += THREADS) live += s_okey[i] != ~0ull;
 	u32 incl = live;
 #pragma unroll
 	for (int off = 1; off < 32; off <<= 1) {
@@ -945,7 +958,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(con
 				o++;
 			}
 		}
-		for (u32 i = tid; i < HR_OVF; i += THREADS) {
+		for (u32 i = tid; i < OVF; i += THREADS) {
 			const u64 k = s_okey[i];
 			if (k != ~0ull) { rec_key[o] = k; rec_cnt[o] = s_ocnt[i]; o++; }
 		}
@@ -1053,10 +1066,130 @@ static int launch_reduce(metro_ctx *ctx, const HitPlan &hp, const u64 *hits, con
 {
 	const size_t smem = ((size_t) WAYS << hp.log_hs) * 8 + (size_t) HR_OVF * 12 + (size_t) (THREADS / 32) * HR_QCAP * 8;
 	CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<WAYS, SUB, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-	hit_reduce_kernel<WAYS, SUB, THREADS><<<HR_MAX_UNITS << (hp.log_hp - hp.log_hs), THREADS, smem, ctx->stream>>>(hits, hit_base, hit_cnt, units, n_units, hp, rec_key, rec_cnt, rec_cap,
+	hit_reduce_kernel<WAYS, SUB, THREADS><<<HR_MAX_UNITS << (hp.log_hp - hp.log_hs), THREADS, smem, ctx->stream>>>(hits, nullptr, hit_base, hit_cnt, units, n_units, hp, rec_key, rec_cnt, rec_cap,
 										   ctx->counters.as<u64>(), ovf);
 	CUDA_TRY(ctx, cudaGetLastError());
 	ctx->launches++;
+	return METRO_OK;
+}
+
+// ---- owner-side pre-reduce of the exchanged records (multi-GPU) -----------------------------------
+// With the tuples sharded by particle ID every (A,B) pair reaches its owner once per shard: the owner of a halo range receives
+// W x its pairs as partial (record, count) entries in arbitrary order.  Instead of pushing all of them through the selection stage's
+// global group-by, they are summed the way pass D counts hits: partitioned by 2048-halo range of the owned halos (one streaming
+// scatter), then one block per range adds the partial counts in its shared-memory (tag, count) ways.  Output: the distinct records
+// of the owned range with summed counts, in the TRANSFORMED form the kernels below work in: the owned halo relative to the range
+// start in the top field, and - for the records routed by haloB - haloA and haloB swapped (RecFmt in select.cu undoes both).
+__device__ __forceinline__ u64 pr_transform(u64 rec, int hb, int tb, int swapped, u32 x_lo)
+{
+	const u64 hm = (1ull << hb) - 1ull, tm = (1ull << (2 * tb)) - 1ull;
+	const u64 B = (rec >> (2 * tb)) & hm, A = (rec >> (2 * tb + hb)) & hm;
+	const u64 X = (swapped ? B : A) - (u64) x_lo, Y = swapped ? A : B;
+	return (X << (hb + 2 * tb)) | (Y << (2 * tb)) | (rec & tm);
+}
+
+__global__ void __launch_bounds__(256) pr_count_kernel(const u64 *__restrict__ rec, i64 n, int hb, int tb, int swapped, u32 x_lo, u32 nbh, u32 *part_cnt)
+{
+	__shared__ u32 sh[HIT_MAX_PARTS];
+	for (u32 i = threadIdx.x; i < nbh; i += 256) sh[i] = 0;
+	__syncthreads();
+	const int sh_x = (swapped ? 0 : hb) + 2 * tb;
+	const u64 hm = (1ull << hb) - 1ull;
+	for (i64 i = (i64) blockIdx.x * 256 + threadIdx.x; i < n; i += (i64) gridDim.x * 256) {
+		const u32 d = ((u32) ((rec[i] >> sh_x) & hm) - x_lo) >> 11;
+		if (d < nbh) atomicAdd(&sh[d], 1u);
+	}
+	__syncthreads();
+	for (u32 i = threadIdx.x; i < nbh; i += 256) if (sh[i]) atomicAdd(&part_cnt[i * CSTRIDE], sh[i]);
+}
+
+// bases of the partitions (exclusive scan of their counts) and the write cursors
+__global__ void __launch_bounds__(HIT_MAX_PARTS) pr_base_kernel(const u32 *__restrict__ part_cnt, u32 nbh, u64 *__restrict__ base, unsigned long long *__restrict__ cursor)
+{
+	__shared__ u64 s_warp[32];
+	const u32 d = threadIdx.x;
+	const u64 c = d < nbh ? part_cnt[d * CSTRIDE] : 0;
+	const u64 b = block_excl_scan_u64(c, s_warp, nullptr);
+	if (d < nbh) { base[d] = b; cursor[d] = b; }
+}
+
+// block-aggregated scatter into the partitions (one global atomic per block and partition), records transformed on the way
+__global__ void __launch_bounds__(256) pr_scatter_kernel(const u64 *__restrict__ rec, const u32 *__restrict__ cnt, i64 n, int hb, int tb, int swapped, u32 x_lo,
+							  u32 nbh, unsigned long long *cursor, u64 *__restrict__ out_key, u32 *__restrict__ out_cnt)
+{
+	__shared__ unsigned long long s_base[HIT_MAX_PARTS];
+	__shared__ u32 s_c[HIT_MAX_PARTS];
+	for (u32 i = threadIdx.x; i < nbh; i += 256) s_c[i] = 0;
+	__syncthreads();
+	const int sh_x = (swapped ? 0 : hb) + 2 * tb;
+	const u64 hm = (1ull << hb) - 1ull;
+	const i64 per = (n + gridDim.x - 1) / gridDim.x;
+	const i64 lo = (i64) blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+	for (i64 i = lo + threadIdx.x; i < hi; i += 256) {
+		const u32 d = ((u32) ((rec[i] >> sh_x) & hm) - x_lo) >> 11;
+		if (d < nbh) atomicAdd(&s_c[d], 1u);
+	}
+	__syncthreads();
+	for (u32 i = threadIdx.x; i < nbh; i += 256) {
+		s_base[i] = s_c[i] ? atomicAdd(&cursor[i], (unsigned long long) s_c[i]) : 0ull;
+		s_c[i] = 0;
+	}
+	__syncthreads();
+	for (i64 i = lo + threadIdx.x; i < hi; i += 256) {
+		const u64 r = rec[i];
+		const u32 d = ((u32) ((r >> sh_x) & hm) - x_lo) >> 11;
+		if (d >= nbh) continue;
+		const unsigned long long p = s_base[d] + atomicAdd(&s_c[d], 1u);
+		out_key[p] = pr_transform(r, hb, tb, swapped, x_lo);
+		out_cnt[p] = cnt[i];
+	}
+}
+
+// records (key, count)[R] whose halo X (A, or B if swapped) lies in [x_lo, x_hi) -> distinct records with summed counts in
+// okey / ocnt (transformed form, see above); *d_total (device) = their number.  W: 6 scratch buffers.  Returns METRO_ERR_UNSUPPORTED
+// (nothing done) when the range does not fit the partition tables.
+int stage_prereduce(metro_ctx *ctx, const u64 *key, const u32 *cnt, i64 R, int halo_bits, int type_bits, bool swapped, i64 x_lo, i64 x_hi, DevBuf *W,
+		    DevBuf &okey, DevBuf &ocnt, u64 *d_total)
+{
+	cudaStream_t st = ctx->stream;
+	const i64 span = x_hi - x_lo;
+	if (span <= 0 || R <= 0 || halo_bits + 2 * type_bits > 31) return METRO_ERR_UNSUPPORTED;
+	const u32 nbh = (u32) div_up<i64>(span, 2048);
+	if (nbh > HIT_MAX_PARTS) return METRO_ERR_UNSUPPORTED;
+	int rc;
+	// W[0]: part_cnt u32[1024*CSTRIDE] | ovf u32 | n_units u32;  W[1]: base u64[1024] + cursor u64[1024] + out counters u64[8];  W[2]: units;
+	// W[3], W[4]: partitioned key / count
+	if ((rc = dev_reserve(ctx, W[0], (size_t) HIT_MAX_PARTS * CSTRIDE * 4 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, W[1], (size_t) HIT_MAX_PARTS * 16 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, W[2], (size_t) HR_MAX_UNITS * 16))) return rc;
+	if ((rc = dev_reserve(ctx, W[3], (size_t) R * 8 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, W[4], (size_t) R * 4 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, okey, (size_t) R * 8 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, ocnt, (size_t) R * 4 + 64))) return rc;
+	u32 *part_cnt = W[0].as<u32>(), *ovf = part_cnt + (size_t) HIT_MAX_PARTS * CSTRIDE, *n_units = ovf + 1;
+	u64 *base = W[1].as<u64>();
+	unsigned long long *cursor = reinterpret_cast<unsigned long long *>(base + HIT_MAX_PARTS);
+	u64 *outc = base + 2 * HIT_MAX_PARTS;                      // [8]: the reduce kernel's counters ([2] = records out)
+	CUDA_TRY(ctx, cudaMemsetAsync(W[0].p, 0, (size_t) HIT_MAX_PARTS * CSTRIDE * 4 + 64, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(outc, 0, 8 * sizeof(u64), st));
+	const int blocks = (int) std::min<i64>(div_up<i64>(R, 256 * 8), (i64) METRO_NUM_SMS_B200 * 8);
+	pr_count_kernel<<<blocks, 256, 0, st>>>(key, R, halo_bits, type_bits, swapped ? 1 : 0, (u32) x_lo, nbh, part_cnt);
+	CUDA_TRY(ctx, cudaGetLastError());
+	pr_base_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(part_cnt, nbh, base, cursor);
+	CUDA_TRY(ctx, cudaGetLastError());
+	pr_scatter_kernel<<<blocks, 256, 0, st>>>(key, cnt, R, halo_bits, type_bits, swapped ? 1 : 0, (u32) x_lo, nbh, cursor, W[3].as<u64>(), W[4].as<u32>());
+	CUDA_TRY(ctx, cudaGetLastError());
+	hit_units_kernel<<<1, HIT_MAX_PARTS, 0, st>>>(part_cnt, nbh, 6u, reinterpret_cast<uint4 *>(W[2].p), n_units);
+	CUDA_TRY(ctx, cudaGetLastError());
+	HitPlan hp;
+	hp.rec_a_shift = halo_bits + 2 * type_bits; hp.log_hp = 11; hp.log_hs = 11; hp.ways = 4; hp.nbh = nbh; hp.slack = 0;
+	const size_t smem = ((size_t) 4 << hp.log_hs) * 8 + (size_t) HR_OVF_W * 12 + (size_t) (HR_THREADS / 32) * HR_QCAP * 12;
+	CUDA_TRY(ctx, cudaFuncSetAttribute(hit_reduce_kernel<4, false, HR_THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	hit_reduce_kernel<4, false, HR_THREADS, true><<<HR_MAX_UNITS, HR_THREADS, smem, st>>>(W[3].as<u64>(), W[4].as<u32>(), base, part_cnt, reinterpret_cast<uint4 *>(W[2].p), n_units, hp,
+											    okey.as<u64>(), ocnt.as<u32>(), (u64) R, outc, ovf);
+	CUDA_TRY(ctx, cudaGetLastError());
+	ctx->launches += 5;
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_total, outc + 2, sizeof(u64), cudaMemcpyDeviceToDevice, st));
 	return METRO_OK;
 }
 
