@@ -548,7 +548,7 @@ def run_ours(args, rank, world, local_rank):
         tuple_in = 12.0 + (1.0 if prm.nptypes > 2 else 0.0)
         spec_k = [("part_kernel<PACK> x2 (pass A: pack + level-1 partition, one launch per catalogue)", (tuple_in + 8.0) * ids_local, 2, "pass_a"),
                   ("part_kernel (pass B: level-2 partition)", 16.0 * ids_local, 1, "pass_b"),
-                  ("bucket_join_kernel (pass C: shared-memory join, hit records out)", 8.0 * ids_local + 8.0 * hits_local, 1, "pass_c"),
+                  ("bucket_join_direct_kernel (pass C: shared-memory join fed by TMA bulk copies, hit records out)", 8.0 * ids_local + 8.0 * hits_local, 1, "pass_c"),
                   ("hit_reduce_kernel (pass D: shared-memory pair count)", 8.0 * hits_local, 1, "pass_d")]
         for (name, nbytes, nl, key), ms in zip(spec_k, per_step):
             ach = nbytes / (ms * 1e-3) / 1e9
@@ -722,6 +722,9 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
 
     one()                                                   # warm-up (allocations)
     ms, d2h, info = timed(steps, narrow)
+    tt = eng.timings()                                      # device timings of the last match of the timed steps
+    match_dev = {"device_ms": tt["total"], "path": tt["path"], "catalogue0_partitioned_under_upload": bool(tt["resident"]),
+                 "pass_abcd_ms": [round(x, 3) for x in tt["sort_pass_ms"][:4]], "select_ms": round(tt["select"], 3)}
     wide = None
     if narrow:                                              # the same with full 64-bit IDs over the bus, for reference
         one(False)
@@ -758,7 +761,7 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
         ids_step = sum(info_c["n_tuples"])
         chain = {"value": ids_step / (statistics.median(c_ms) * 1e-3), "unit": UNIT, "ms_per_step": statistics.median(c_ms),
                  "ms_all_steps": [round(x, 1) for x in c_ms], "device_match_ms": statistics.median(c_dev),
-                 "note": "median over the steps; the first step re-plans and re-allocates (catalogue 0 has grown by the token tuples)",
+                 "note": "median over the steps; a step re-plans (resident = 0) when catalogue 0, grown by the token tuples this ping-pong chain accumulates, exceeds the 1/8 head room of the plan",
                  "steps_path_resident_passABCD_select_ms": c_res, "h2d_bytes_per_step": int(c_h2d), "steps": n_chain,
                  "ids_per_step": int(ids_step), "per_rank": True,
                  "path": "metro_shift -> metro_catalogue_upload_csr (one catalogue) -> metro_match_pair -> metro_result_fetch"}
@@ -767,7 +770,7 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
     return {"value": ids_glob / (ms / steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": ms / steps, "steps": steps, "n_trees": info["n_trees"], "chain_step": chain,
             "h2d_gbs": h2d / (ms / steps * 1e-3) / 1e9, "ids_over_the_bus": "u32 offsets from the smallest ID" if narrow else "u64",
-            "u64_ids": wide,
+            "u64_ids": wide, "match": match_dev,
             "path": ("metro_catalogue_upload_csr32 x2 (pinned host: particle IDs grouped by halo as u32 offsets + i64 halo offsets; chunked copy, "
                      "widened and range-checked on the device under the copy)" if narrow else
                      "metro_catalogue_upload_csr x2 (pinned host: u64 particle IDs grouped by halo + i64 offsets)") +

@@ -79,6 +79,8 @@ int metro_ctx_create(int device, metro_ctx **out)
 	bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
 	ctx->stream = ctx->own_stream;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaStreamCreateWithFlags(&ctx->eager_stream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_eager, cudaEventDisableTiming) == cudaSuccess;
 	for (int i = 0; ok && i < 5; i++) ok = cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming) == cudaSuccess;
 	for (int i = 0; ok && i < 16; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
 	for (int i = 0; ok && i < SORT_MAX_PASSES + 1; i++) ok = cudaEventCreate(&ctx->ev_pass[i]) == cudaSuccess;
@@ -97,6 +99,7 @@ int metro_ctx_set_stream(metro_ctx *ctx, void *cuda_stream)
 {
 	if (!ctx) return METRO_ERR_INVALID;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	partition_eager_join(ctx);
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 	ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
 	return METRO_OK;
@@ -113,6 +116,7 @@ void metro_ctx_destroy(metro_ctx *ctx)
 {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
+	if (ctx->eager_stream) cudaStreamSynchronize(ctx->eager_stream);
 	cudaStreamSynchronize(ctx->stream);
 	free_catalogue(ctx->cat[0]); free_catalogue(ctx->cat[1]);
 	DevResult &r = ctx->res;
@@ -128,6 +132,8 @@ void metro_ctx_destroy(metro_ctx *ctx)
 	for (int i = 0; i < SORT_MAX_PASSES + 1; i++) cudaEventDestroy(ctx->ev_pass[i]);
 	for (int i = 0; i < 5; i++) if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+	if (ctx->eager_stream) cudaStreamDestroy(ctx->eager_stream);
+	if (ctx->ev_eager) cudaEventDestroy(ctx->ev_eager);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -261,6 +267,8 @@ static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, cons
 {
 	int rc;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	// (an upload into slot 1 does not wait for the eager partition of catalogue 0: that overlap is its purpose)
+	if (slot == 0 && (rc = partition_eager_join(ctx))) return rc;
 	DevCatalogue &c = ctx->cat[slot];
 	c.valid = false; c.b_pid = nullptr; c.b_halo = nullptr; c.b_type = nullptr;
 	if ((rc = upload_halos(ctx, c, prm, cat))) return rc;
@@ -319,6 +327,8 @@ static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, cons
 	c.valid = true;
 	ctx->nptypes = prm->nptypes;
 	ctx->res.valid = false;
+	// catalogue 0 of a pair: partition it now, under the upload of catalogue 1
+	if (slot == 0) return stage_partition_eager(ctx, prm);
 	return METRO_OK;
 }
 
@@ -362,6 +372,7 @@ int metro_catalogue_adopt_device(metro_ctx *ctx, int slot, const metro_params *p
 	int rc = check_catalogue(ctx, slot, prm, cat);
 	if (rc) return rc;
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	if ((rc = partition_eager_join(ctx))) return rc;
 	DevCatalogue &c = ctx->cat[slot];
 	c.valid = false;
 	if ((rc = upload_halos(ctx, c, prm, cat))) return rc;
@@ -385,6 +396,7 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 	if (!ctx->cat[0].valid || !ctx->cat[1].valid) { metro_set_error(ctx, "both catalogues must be uploaded before metro_match_pair"); return METRO_ERR_STATE; }
 	if (prm->nptypes != ctx->nptypes) { metro_set_error(ctx, "nptypes differs from the uploaded catalogues"); return METRO_ERR_INVALID; }
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	if ((rc = partition_eager_join(ctx))) return rc;
 	cudaStream_t st = ctx->stream;
 	DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
 	const i64 N = c0.n_tuples + c1.n_tuples;
@@ -603,6 +615,7 @@ int metro_shift(metro_ctx *ctx, const metro_params *prm)
 	if (rc) return rc;
 	if (!ctx->res.valid) { metro_set_error(ctx, "metro_shift needs the result of metro_match_pair (token halos)"); return METRO_ERR_STATE; }
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	if ((rc = partition_eager_join(ctx))) return rc;
 	return stage_shift(ctx, prm);
 }
 

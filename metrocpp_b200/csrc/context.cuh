@@ -83,6 +83,9 @@ struct metro_ctx {
 	cudaStream_t stream = nullptr;       // stream in use
 	cudaStream_t own_stream = nullptr;   // the context's private stream
 	cudaStream_t copy_stream = nullptr;  // host -> device copies of an upload (overlapped with the per-chunk checks on `stream`)
+	cudaStream_t eager_stream = nullptr; // passes A and B of catalogue 0 while catalogue 1 is being uploaded (stage_partition_eager)
+	cudaEvent_t ev_eager = nullptr;
+	bool eager_pending = false;
 	cudaEvent_t ev_up[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	char err[1024] = {0};
 	int nptypes = 0;
@@ -126,7 +129,9 @@ int scan_exclusive_u32(metro_ctx *ctx, cudaStream_t st, const u32 *in, u32 *out,
 // ---- pipeline stages -----------------------------------------------------------------------------
 int stage_pack_hist(metro_ctx *ctx, const KeyLayout &L, const SortPlan &plan);      // join.cu
 
-bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap, int finer);     // partjoin.cu
+bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap, int finer, i64 nmax_known = -1);     // partjoin.cu
+int stage_partition_eager(metro_ctx *ctx, const metro_params *prm);
+int partition_eager_join(metro_ctx *ctx);
 int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back,
 			 u32 *overflow_mask, bool finer_plan);
 int stage_prereduce(metro_ctx *ctx, const u64 *key, const u32 *cnt, i64 R, int halo_bits, int type_bits, bool swapped, i64 x_lo, i64 x_hi, DevBuf *W,

@@ -974,14 +974,16 @@ static size_t part_smem(int nb) { return (size_t) PT_TILE * 8 + (size_t) nb * 16
 // Is the partition path applicable, and with which bucket bits?
 // finer: halve the buckets `finer` times (the retry after a bucket's table or hit staging overflowed: catalogues whose
 // particles have many memberships produce more hits per key than the default bucket size provides for)
-bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap, int finer)
+// nmax_known >= 0: the tuples of the larger catalogue (the eager partition of catalogue 0 plans before catalogue 1 exists)
+bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap, int finer, i64 nmax_known)
 {
-	static const i64 min_n = getenv("METRO_PART_MIN_N") ? atoll(getenv("METRO_PART_MIN_N")) : (1ll << 23);
+	const char *env_min = getenv("METRO_PART_MIN_N");                // (read per call: the tests change it inside one process)
+	const i64 min_n = env_min ? atoll(env_min) : (1ll << 23);
 	if (N < min_n || L.pid_bits < 16) return false;                 // small pairs: the LSD path is fine
 	if (L.halo_bits + 2 * L.type_bits > 31) return false;           // the pass-D way tag (B, tA, tB) is 31 bits
 	if (ctx->cat[0].n_halos > ((i64) HIT_MAX_PARTS << (11 + HR_MAX_SUB_LOG))) return false;
 	int tb = 0;
-	const i64 nmax = std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
+	const i64 nmax = nmax_known >= 0 ? nmax_known : std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
 	while ((nmax >> tb) > 3900 && tb < 20) tb++;                    // final buckets of 2-4 k keys per catalogue
 	// dense IDs: up to two more bucket bits if that leaves BD_DIRECT_RB residual pid bits, the width at which pass C runs its
 	// direct-address table at two CTAs per SM (catalogues in which fewer than half of the particle IDs are bound)
@@ -1193,6 +1195,43 @@ int stage_prereduce(metro_ctx *ctx, const u64 *key, const u32 *cnt, i64 R, int h
 	return METRO_OK;
 }
 
+// Buffers and small state of one partition join; a function of the plan and of catalogue 0 alone, so that the eager partition of
+// catalogue 0 (stage_partition_eager) and the join proper lay them out alike.
+struct PartState {
+	u64 nbk, nb1, nb, hits_cap;
+	HitPlan hp;
+	u32 *g1, *hit_cnt, *t0, *g2, *hit_cap, *ovf, *n_units;
+	u64 *hit_base;
+	uint4 *units;
+};
+
+static int part_state_reserve(metro_ctx *ctx, const PartPlan &P, int rec_halo_bits, int type_bits, PartState *S)
+{
+	const DevCatalogue &c0 = ctx->cat[0];
+	S->nbk = 1ull << (P.b1 + P.b2);                                        // buckets per catalogue
+	S->nb1 = 2 * (1ull << P.b1) * P.r1; S->nb = 2 * S->nbk;                 // level-1 regions, final buckets (both catalogues)
+	S->hp = make_hit_plan(rec_halo_bits, type_bits, c0.n_halos);
+	// 2 hits per catalogue-0 tuple + the per-range slack; the tuple counts are sampled (every HIST_SAMPLE-th tile, scaled) by up to two
+	// streams (resident part: hit_hist_kernel; the rest: pass A), each over-estimating by up to HIST_SAMPLE tiles
+	S->hits_cap = 2ull * ((u64) c0.n_tuples + 2ull * HIST_SAMPLE * PT_TILE) + (u64) (S->hp.slack + 2) * S->hp.nbh;
+	int rc;
+	// keys_a: level-1 regions, dead after pass B and reused for the hit regions
+	if ((rc = dev_reserve(ctx, ctx->keys_a, (std::max((size_t) S->nb1 * P.cap1, (size_t) S->hits_cap) + PT_TILE) * 8 + 64))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->keys_b, ((size_t) S->nb * P.cap2 + PT_TILE) * 8 + 64))) return rc;
+	// small state: [g1 nb1*CSTRIDE][hit_cnt 1024*CSTRIDE][t0 1024*CSTRIDE][g2 nb][hit_cap 1024][ovf, n_units, pad..16] u32, then hit_base u64[1024],
+	// units uint4[HR_MAX_UNITS]
+	const size_t n32 = (size_t) S->nb1 * CSTRIDE + 2 * (size_t) HIT_MAX_PARTS * CSTRIDE + S->nb + HIT_MAX_PARTS + 16;
+	const size_t off_base = (n32 * 4 + 15) & ~(size_t) 15;
+	const size_t off_units = off_base + (size_t) HIT_MAX_PARTS * 8;
+	if ((rc = dev_reserve(ctx, ctx->part_counts, off_units + (size_t) HR_MAX_UNITS * 16))) return rc;
+	S->g1 = ctx->part_counts.as<u32>(); S->hit_cnt = S->g1 + S->nb1 * CSTRIDE; S->t0 = S->hit_cnt + (size_t) HIT_MAX_PARTS * CSTRIDE;
+	S->g2 = S->t0 + (size_t) HIT_MAX_PARTS * CSTRIDE; S->hit_cap = S->g2 + S->nb;
+	S->ovf = S->hit_cap + HIT_MAX_PARTS; S->n_units = S->ovf + 1;
+	S->hit_base = reinterpret_cast<u64 *>(ctx->part_counts.as<unsigned char>() + off_base);
+	S->units = reinterpret_cast<uint4 *>(ctx->part_counts.as<unsigned char>() + off_units);
+	return METRO_OK;
+}
+
 // Whole front end of a pair on the partition path: records (scratch[0] = key u64[R], scratch[1] =
 // count u32[R]; the same pair may appear more than once).  *fell_back = true: an overflow flag was
 // raised (nothing usable was produced; the caller runs the LSD path).  Timing events: ev[1] after
@@ -1206,29 +1245,17 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	cudaStream_t st = ctx->stream;
 	*fell_back = false;
 	const DevCatalogue &c0 = ctx->cat[0], &c1 = ctx->cat[1];
-	const u64 nbk = 1ull << (P.b1 + P.b2);                                 // buckets per catalogue
-	const u64 nb1 = 2 * (1ull << P.b1) * P.r1, nb = 2 * nbk;                // level-1 regions, final buckets (both catalogues)
-	const HitPlan hp = make_hit_plan(rec_halo_bits, L.type_bits, c0.n_halos);
-	// 2 hits per catalogue-0 tuple + the per-range slack; the tuple counts are sampled (every HIST_SAMPLE-th tile, scaled) by up to two
-	// streams (resident part: hit_hist_kernel; the rest: pass A), each over-estimating by up to HIST_SAMPLE tiles
-	const u64 hits_cap = 2ull * ((u64) c0.n_tuples + 2ull * HIST_SAMPLE * PT_TILE) + (u64) (hp.slack + 2) * hp.nbh;
-	const u64 rec_cap = 16ull * (u64) (c0.n_halos + c1.n_halos) + (1ull << 20);
+	PartState S;
 	int rc;
-	// keys_a: level-1 regions, dead after pass B and reused for the hit regions
-	if ((rc = dev_reserve(ctx, ctx->keys_a, (std::max((size_t) nb1 * P.cap1, (size_t) hits_cap) + PT_TILE) * 8 + 64))) return rc;
-	if ((rc = dev_reserve(ctx, ctx->keys_b, ((size_t) nb * P.cap2 + PT_TILE) * 8 + 64))) return rc;
+	if ((rc = part_state_reserve(ctx, P, rec_halo_bits, L.type_bits, &S))) return rc;
+	const u64 nbk = S.nbk, nb1 = S.nb1, hits_cap = S.hits_cap;
+	const HitPlan hp = S.hp;
+	const u64 rec_cap = 16ull * (u64) (c0.n_halos + c1.n_halos) + (1ull << 20);
 	if ((rc = dev_reserve(ctx, ctx->scratch[0], (size_t) rec_cap * sizeof(u64)))) return rc;
 	if ((rc = dev_reserve(ctx, ctx->scratch[1], (size_t) rec_cap * sizeof(u32)))) return rc;
-	// small state: [g1 nb1*CSTRIDE][hit_cnt 1024*CSTRIDE][t0 1024*CSTRIDE][g2 nb][hit_cap 1024][ovf, n_units, pad..16] u32, then hit_base u64[1024],
-	// units uint4[HR_MAX_UNITS]
-	const size_t n32 = (size_t) nb1 * CSTRIDE + 2 * (size_t) HIT_MAX_PARTS * CSTRIDE + nb + HIT_MAX_PARTS + 16;
-	const size_t off_base = (n32 * 4 + 15) & ~(size_t) 15;
-	const size_t off_units = off_base + (size_t) HIT_MAX_PARTS * 8;
-	if ((rc = dev_reserve(ctx, ctx->part_counts, off_units + (size_t) HR_MAX_UNITS * 16))) return rc;
-	u32 *g1 = ctx->part_counts.as<u32>(), *hit_cnt = g1 + nb1 * CSTRIDE, *t0 = hit_cnt + (size_t) HIT_MAX_PARTS * CSTRIDE, *g2 = t0 + (size_t) HIT_MAX_PARTS * CSTRIDE, *hit_cap = g2 + nb;
-	u32 *ovf = hit_cap + HIT_MAX_PARTS, *n_units = ovf + 1;
-	u64 *hit_base = reinterpret_cast<u64 *>(ctx->part_counts.as<unsigned char>() + off_base);
-	uint4 *units = reinterpret_cast<uint4 *>(ctx->part_counts.as<unsigned char>() + off_units);
+	u32 *g1 = S.g1, *hit_cnt = S.hit_cnt, *t0 = S.t0, *g2 = S.g2, *hit_cap = S.hit_cap, *ovf = S.ovf, *n_units = S.n_units;
+	u64 *hit_base = S.hit_base;
+	uint4 *units = S.units;
 	u64 *counters = ctx->counters.as<u64>();
 	PartResident &R = ctx->resident;
 	const int half0 = reuse0 ? R.half0 : 0, half1 = 1 - half0;          // halves of keys_b / g2 that hold catalogue 0 / 1
@@ -1326,5 +1353,71 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	ctx->res.info.n_table_hits = (i64) ctx->h_counters[5];
 	// the buckets of catalogue 1 stay: after metro_shift they are the buckets of the next pair's catalogue 0
 	R.cat1 = true; R.gen = c1.gen; R.half0 = half0; R.half1 = half1; R.P = P; R.L = L; R.pid_base = ctx->pid_base;
+	return METRO_OK;
+}
+
+// Eager partition of catalogue 0 (called at the end of its upload): passes A and B of its tuples run on the context's side stream
+// while the caller is still sending catalogue 1 over the bus; the pair then starts with catalogue 0's buckets resident, exactly like
+// the second pair of a chain.  Layout and plan are guessed from catalogue 0 alone (same ID range, at most 1/8 more tuples, at most
+// twice the halos in catalogue 1); if the pair does not fit them, metro_match_pair plans afresh and this work is lost, nothing else.
+int stage_partition_eager(metro_ctx *ctx, const metro_params *prm)
+{
+	static const bool off = (getenv("METRO_NO_EAGER") && atoi(getenv("METRO_NO_EAGER"))) || (getenv("METRO_FORCE_LSD") && atoi(getenv("METRO_FORCE_LSD"))) ||
+				(getenv("METRO_NO_RESIDENT") && atoi(getenv("METRO_NO_RESIDENT")));
+	PartResident &R = ctx->resident;
+	const DevCatalogue &c0 = ctx->cat[0];
+	R.cat0 = false; R.cat1 = false;
+	if (off || !c0.valid || c0.n_tuples <= 0 || c0.n_halos <= 0 || !ctx->eager_stream) return METRO_OK;
+	u64 pid_base = c0.min_pid;
+	const int pid_bits = std::max(1, ceil_log2_u64(c0.max_pid - pid_base));
+	{	// the same preference as metro_match_pair: base 0, else a multiple of 2^pid_bits, when it costs no key bit
+		const u64 aligned = pid_bits < 64 ? (pid_base >> pid_bits) << pid_bits : 0;
+		if (std::max(1, ceil_log2_u64(c0.max_pid)) <= pid_bits) pid_base = 0;
+		else if (std::max(1, ceil_log2_u64(c0.max_pid - aligned)) <= pid_bits) pid_base = aligned;
+	}
+	const int halo_bits = std::max(1, ceil_log2_u64((u64) (c0.n_halos - 1)));
+	const int type_bits = prm->nptypes > 1 ? ceil_log2_u64((u64) prm->nptypes - 1) : 0;
+	if (2 * halo_bits + 2 * type_bits > 63 || halo_bits + type_bits > 31 || pid_bits + 1 + halo_bits + type_bits > 64) return METRO_OK;
+	const int hb = (halo_bits + 1 + 2 * type_bits <= 31 && pid_bits + 2 + halo_bits + type_bits <= 64) ? halo_bits + 1 : halo_bits;
+	const KeyLayout L = make_key_layout(pid_bits, hb, type_bits);
+	PartPlan P;
+	i64 ncap = 0;
+	if (!partition_join_plan(ctx, L, 2 * c0.n_tuples, &P, &ncap, ctx->part_finer, c0.n_tuples)) return METRO_OK;
+	cudaStream_t keep = ctx->stream;
+	ctx->stream = ctx->eager_stream;                                     // launch_part and dev_reserve work on ctx->stream
+	const u64 keep_base = ctx->pid_base;
+	ctx->pid_base = pid_base;
+	int rc = METRO_OK;
+	do {
+		cudaStream_t st = ctx->stream;
+		PartState S;
+		if ((rc = part_state_reserve(ctx, P, halo_bits, type_bits, &S))) break;
+		if (cudaMemsetAsync(S.g1, 0, (size_t) (S.hit_cap - S.g1) * 4 + (size_t) (HIT_MAX_PARTS + 16) * 4, st) != cudaSuccess) { rc = METRO_ERR_CUDA; break; }
+		if ((rc = launch_part<true>(ctx, P.b1, (unsigned) div_up<i64>(c0.n_tuples, PT_TILE), c0.d_pid(), c0.d_halo(), c0.d_type(), (u64) c0.n_tuples, 0u, L, P,
+					    ctx->keys_a.as<u64>(), nullptr, S.g1, S.ovf, nullptr, S.hp))) break;
+		if ((rc = launch_part<false>(ctx, P.b2, (unsigned) (S.nb1 * P.tiles1), ctx->keys_a.as<u64>(), nullptr, nullptr, 0, 0, L, P, ctx->keys_b.as<u64>(), S.g1, S.g2,
+					     S.ovf, nullptr, S.hp))) break;
+		ctx->h_counters[61] = ~0ull;
+		if (cudaMemcpyAsync(ctx->h_counters + 61, S.ovf, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaEventRecord(ctx->ev_eager, st) != cudaSuccess) {
+			rc = METRO_ERR_CUDA;
+			break;
+		}
+		ctx->eager_pending = true;
+		R.cat0 = true; R.gen = c0.gen; R.half0 = 0; R.half1 = 1; R.P = P; R.L = L; R.pid_base = pid_base; R.nmax_cap = ncap; R.tail0 = c0.n_tuples;
+	} while (0);
+	ctx->stream = keep;
+	ctx->pid_base = keep_base;
+	if (rc == METRO_ERR_CUDA) metro_set_error(ctx, "eager partition of catalogue 0: %s", cudaGetErrorString(cudaGetLastError()));
+	return rc;
+}
+
+// Before anything touches catalogue 0, the key buffers or the resident state: wait for the eager partition and drop its buckets if a
+// region overflowed.
+int partition_eager_join(metro_ctx *ctx)
+{
+	if (!ctx->eager_pending) return METRO_OK;
+	ctx->eager_pending = false;
+	CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_eager));
+	if ((u32) ctx->h_counters[61] != 0) ctx->resident.cat0 = false;
 	return METRO_OK;
 }

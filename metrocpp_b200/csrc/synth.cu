@@ -180,8 +180,11 @@ extern "C" int metro_synth_pair_device(metro_ctx *ctx, const metro_params *prm, 
 	if (!ctx || !prm || !spec) return METRO_ERR_INVALID;
 	if (prm->nptypes < 1 || prm->nptypes > 8) { metro_set_error(ctx, "nptypes out of range"); return METRO_ERR_INVALID; }
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+	int rc = partition_eager_join(ctx);
+	if (rc) return rc;
+	ctx->resident.cat0 = false; ctx->resident.cat1 = false;
 	HostTable HT;
-	int rc = build_table(spec, prm->nptypes, HT, ctx->err, sizeof ctx->err);
+	rc = build_table(spec, prm->nptypes, HT, ctx->err, sizeof ctx->err);
 	if (rc) return rc;
 	cudaStream_t st = ctx->stream;
 	const int T = prm->nptypes;

@@ -36,16 +36,18 @@ def split(rng, ids, n_halos, alpha=1.0):
     return np.split(ids, cuts[:-1])
 
 
-def run_case(eng, name, c0, c1, prm, expect_path=None):
-    eng.upload(0, prm, c0)
+def run_case(eng, name, c0, c1, prm, expect_path=None, expect_resident=None):
+    eng.upload(0, prm, c0)          # large enough for the partition path: passes A and B of catalogue 0 start here (eager partition)
     eng.upload(1, prm, c1)
     res = eng.find_progenitors_and_clean(prm)
-    path = eng.timings()["path"]
+    path, resident = eng.timings()["path"], eng.timings()["resident"]
     oprm = binding.Params(prm.nptypes, prm.min_part_cmp, prm.min_part_halo, prm.fac_orphan_steps, prm.max_orphan_steps, prm.flavour)
     compare_result_with_oracle(res, binding.match_pair(oprm, to_oracle_catalogue(c0), to_oracle_catalogue(c1)))
     if expect_path is not None:
         assert path == expect_path, (name, path, expect_path)
-    print(f"CASE {name} path={path} hits={res.info['n_hits']} pairs={res.info['n_pairs']} ok", flush=True)
+    if expect_resident is not None:
+        assert resident == expect_resident, (name, resident, expect_resident)
+    print(f"CASE {name} path={path} eager={resident} hits={res.info['n_hits']} pairs={res.info['n_pairs']} ok", flush=True)
 
 
 def main():
@@ -59,7 +61,8 @@ def main():
     later = split(rng, ids, 800)
     earlier = [x[: int(0.9 * len(x))] for x in later]
     order = rng.permutation(len(earlier))
-    run_case(eng, "plain", catalogue(later, 10**6, rng), catalogue([earlier[i] for i in order], 2 * 10**6, rng), prm, expect_path=1)
+    run_case(eng, "plain", catalogue(later, 10**6, rng), catalogue([earlier[i] for i in order], 2 * 10**6, rng), prm, expect_path=1,
+             expect_resident=0 if os.environ.get("METRO_NO_EAGER") == "1" else 1)
 
     # 1b. hashed 64-bit particle IDs (pid + snap + halo + type do not fit one 64-bit key): the wide-key front end; the
     #     trees must be those of the same pair with narrow IDs (only the equality of IDs matters)
@@ -72,9 +75,11 @@ def main():
     big1 = [x[: int(0.95 * len(x))] for x in big]
     run_case(eng, "dominant_halo", catalogue(big, 10**6, rng), catalogue(big1, 2 * 10**6, rng), prm, expect_path=1)
 
-    # 3. earlier catalogue 4x larger than the later one (fresh particles in extra halos)
+    # 3. earlier catalogue 4x larger than the later one (fresh particles in extra halos, IDs beyond the later catalogue's range): the
+    #    eagerly built buckets of catalogue 0 do not fit the pair and are dropped
     extra = (np.arange(3 * n, dtype=np.uint64) + np.uint64(1 << 23))
-    run_case(eng, "unbalanced", catalogue(later, 10**6, rng), catalogue(earlier + split(rng, extra, 1500), 2 * 10**6, rng), prm, expect_path=1)
+    run_case(eng, "unbalanced", catalogue(later, 10**6, rng), catalogue(earlier + split(rng, extra, 1500), 2 * 10**6, rng), prm, expect_path=1,
+             expect_resident=0)
 
     # 4. nesting: every particle of the earlier catalogue is a member of 3 halos (3 hits per catalogue-0 tuple): stays on the
     #    partition path (the hit ranges of a small catalogue carry enough slack), same answer
@@ -138,9 +143,9 @@ def main():
         engine_run_chain(eng, chain, {"minPartHalo": 30, "minPartCmp": 10, "facOrphanSteps": 15, "maxOrphanSteps": 3}, flavour,
                          on_step=lambda e, r: steps.append((e.timings()["path"], e.timings()["resident"], r.info["n_tokens"])))
         assert len(steps) == 5 and all(p == 1 for p, _, _ in steps), steps
-        # resident from the second pair on, unless the catalogue outgrows the plan (the ZOOM flavour doubles the token tuples
-        # at every orphan step: src/MergerTree.cpp:597-603)
-        assert steps[0][1] == 0 and sum(r for _, r, _ in steps[1:]) >= (3 if flavour == "gather" else 1), steps
+        # resident from the second pair on (and, with the eager partition, in the first), unless the catalogue outgrows the plan (the
+        # ZOOM flavour doubles the token tuples at every orphan step: src/MergerTree.cpp:597-603)
+        assert sum(r for _, r, _ in steps[1:]) >= (3 if flavour == "gather" else 1), steps
         assert sum(t for _, _, t in steps) > 0, steps                                  # token tuples were appended to resident buckets
         print(f"CASE resident_chain_{flavour} steps={steps} ok", flush=True)
 
