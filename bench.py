@@ -55,6 +55,8 @@ def parse_args():
                     help="pair: the headline 1024^3 pair (default).  chain20 / lgf54: BASELINE.json configs[4] / [3] - whole snapshot chains of distinct "
                          "synthetic catalogues through upload -> match -> fetch -> shift, one GPU")
     ap.add_argument("--chain-scale", type=float, default=1.0, help="scale factor on the halo and tuple counts of a chain workload")
+    ap.add_argument("--sweep", default="", help="chain workloads, tuning only: NAME=v1,v2,... runs the chain once per value of that library "
+                                                "environment switch (stderr: one line per value) before the measured default run")
     ap.add_argument("--ref-sample", type=int, default=400_000)
     ap.add_argument("--ref-ids", type=int, default=10_000_000, help="bound IDs per snapshot of the pair the multi-rank reference arm matches per step")
     return ap.parse_args()
@@ -857,6 +859,17 @@ def run_chain_workload(args):
                           "passes_ms": [round(x, 3) for x in tm["sort_pass_ms"][:4]], "select_ms": round(tm["select"], 3),
                           "h2d_bytes": cats[k][1].numel() * cats[k][1].element_size() + cats[k][2].numel() * 8 + (cats[k][3] if w["multi"] else 0)})
         return steps
+    if args.sweep:                                           # tuning: the same chain under several values of one library switch
+        name, vals = args.sweep.split("=")
+        for v in vals.split(","):
+            os.environ[name] = v
+            run_chain()
+            st = run_chain()
+            mean = lambda f: round(statistics.mean(f(x) for x in st), 3)
+            print(f"[sweep] {name}={v}: device {mean(lambda x: x['device_ms'])} ms/pair, wall {mean(lambda x: x['wall_ms'])}, passes A-D "
+                  f"{[mean(lambda x, i=i: x['passes_ms'][i]) for i in range(4)]}, select {mean(lambda x: x['select_ms'])}, "
+                  f"resident {sum(x['resident'] for x in st)}/{len(st)}, partition path {sum(x['path'] == 1 for x in st)}", file=sys.stderr, flush=True)
+        os.environ.pop(name, None)
     run_chain()                                              # warm-up: allocations, plans
     sampler = ClockSampler(0)
     sampler.start()

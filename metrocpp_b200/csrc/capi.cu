@@ -1,4 +1,5 @@
 // capi.cu -- the extern "C" boundary (include/metro_b200.h) and the per-pair pipeline driver.
+#include <chrono>
 #include <stdlib.h>
 
 #include "context.cuh"
@@ -22,10 +23,15 @@ int dev_reserve(metro_ctx *ctx, DevBuf &b, size_t bytes)
 	// chain; without head room that costs a cudaFree + cudaMalloc (tens of ms, and a stall of every rank of a multi-GPU
 	// run in the next collective) per buffer
 	if (b.p || bytes < (1ull << 30)) bytes += bytes / 4 + 4096;
+	static const bool dbg = getenv("METRO_DEBUG_ALLOC") != nullptr;
+	const auto t0 = std::chrono::steady_clock::now();
+	const size_t old = b.cap;
 	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 	if (bytes < 256) bytes = 256;
 	CUDA_TRY(ctx, cudaMalloc(&b.p, bytes));
 	b.cap = bytes;
+	if (dbg) fprintf(stderr, "[metro] dev_reserve %zu -> %zu bytes, %.3f ms\n", old, bytes,
+			 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 	return METRO_OK;
 }
 

@@ -969,6 +969,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) hit_reduce_kernel(con
 	if (ovf) atomicOr(overflow, 16u);
 }
 
+#define PART_MIN_BITS 5            // fewest bucket bits of one partition level (part_kernel<32>)
 static size_t part_smem(int nb) { return (size_t) PT_TILE * 8 + (size_t) nb * 16 + (size_t) HIT_MAX_PARTS * 4; }
 
 // Is the partition path applicable, and with which bucket bits?
@@ -985,15 +986,22 @@ bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPl
 	int tb = 0;
 	const i64 nmax = nmax_known >= 0 ? nmax_known : std::max(ctx->cat[0].n_tuples, ctx->cat[1].n_tuples);
 	while ((nmax >> tb) > 3900 && tb < 20) tb++;                    // final buckets of 2-4 k keys per catalogue
-	// dense IDs: up to two more bucket bits if that leaves BD_DIRECT_RB residual pid bits, the width at which pass C runs its
-	// direct-address table at two CTAs per SM (catalogues in which fewer than half of the particle IDs are bound)
-	if (L.pid_bits - tb > BD_DIRECT_RB && L.pid_bits - tb <= BD_DIRECT_RB + 2 && L.pid_bits - BD_DIRECT_RB <= 20) tb = L.pid_bits - BD_DIRECT_RB;
+	// dense IDs: one more bucket bit if that leaves BD_DIRECT_RB residual pid bits, the width at which pass C runs its direct-address
+	// table at two CTAs per SM (1e9-tuple shard with 2^31 IDs: 6.5 ms instead of 8.4 with the 64 KB table of 14 residual bits).  Two
+	// more bits do not pay: quarter-filled buckets cost more than the hashed table on full ones (zoom chain, 15 residual bits:
+	// pass C 0.35 ms direct at +2 bits, 0.29 ms at +1 with the 64 KB table, 0.19 ms hashed at +0)
+	if (L.pid_bits - tb == BD_DIRECT_RB + 1 && L.pid_bits - BD_DIRECT_RB <= 20) tb = L.pid_bits - BD_DIRECT_RB;
+	const char *env_tb = getenv("METRO_TB");                         // experiments: total bucket bits
+	if (env_tb && atoi(env_tb) > 0) tb = atoi(env_tb);
 	tb = std::min(tb + finer, 20);
+	// at least 32 buckets per level (catalogues of 10^7 tuples: 2^12 buckets of 2-4 k keys, not 2^16 of 150 - a pass-C block costs
+	// about 10 ns before it has seen a key)
+	tb = std::max(tb, 2 * PART_MIN_BITS);
 	PartPlan P;
 	P.b1 = getenv("METRO_B1") ? atoi(getenv("METRO_B1")) : (tb > 18 ? tb - 9 : (tb + 1) / 2);
 	P.b2 = tb - P.b1;
-	if (P.b1 < 8) P.b1 = 8;
-	if (P.b2 < 8) P.b2 = 8;
+	if (P.b1 < PART_MIN_BITS) P.b1 = PART_MIN_BITS;
+	if (P.b2 < PART_MIN_BITS) P.b2 = PART_MIN_BITS;
 	if (P.b1 > 10 || P.b2 > 10 || P.b1 + P.b2 > L.pid_bits) return false;
 	P.pid_bits = L.pid_bits;
 	P.shift1 = L.pid_shift + L.pid_bits - P.b1;
@@ -1053,7 +1061,7 @@ static int launch_part(metro_ctx *ctx, int bits, unsigned grid, const u64 *in, c
 		break;                                                                                                              \
 	}
 	switch (1 << bits) {
-		PART_CASE(256) PART_CASE(512) PART_CASE(1024)
+		PART_CASE(32) PART_CASE(64) PART_CASE(128) PART_CASE(256) PART_CASE(512) PART_CASE(1024)
 	default: metro_set_error(ctx, "unsupported partition width 2^%d", bits); return METRO_ERR_UNSUPPORTED;
 	}
 #undef PART_CASE

@@ -7,6 +7,7 @@
 //                                                           second merit sort
 // Work is O(M) with M = distinct (haloA, haloB) pairs (a few per halo), i.e. negligible next to
 // the tuple sort; every step is a flat data-parallel kernel, a scan or a small radix sort.
+#include <chrono>
 #include "context.cuh"
 
 // ---- merit: bit-exact restatement of SortByMerit's arithmetic --------------------------------
@@ -602,10 +603,12 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	static bool pev_ok = false;
 	int n_mark = 0;
 	const char *mark_name[16];
+	double mark_host[16];
 	auto MARK = [&](const char *name) {
 		if (!prof || ctx->rank != 0 || n_mark >= 16) return;
 		if (!pev_ok) { for (auto &e : pev) cudaEventCreate(&e); pev_ok = true; }
 		mark_name[n_mark] = name;
+		mark_host[n_mark] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 		cudaEventRecord(pev[n_mark++], st);
 	};
 	MARK("start");
@@ -759,7 +762,7 @@ int stage_select(metro_ctx *ctx, const metro_params *prm, const KeyLayout &KL, c
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	if (n_mark > 1) {
 		fprintf(stderr, "[metro] select (RA %lld RB %lld nA %lld nB %lld H0 %lld):", (long long) RA, (long long) RB, (long long) nA, (long long) nB, (long long) H0);
-		for (int i = 1; i < n_mark; i++) { float ms = 0; cudaEventElapsedTime(&ms, pev[i - 1], pev[i]); fprintf(stderr, " %s %.3f ms;", mark_name[i], ms); }
+		for (int i = 1; i < n_mark; i++) { float ms = 0; cudaEventElapsedTime(&ms, pev[i - 1], pev[i]); fprintf(stderr, " %s %.3f ms (host %.3f);", mark_name[i], ms, mark_host[i] - mark_host[i - 1]); }
 		fprintf(stderr, "\n");
 	}
 	const u64 *h = ctx->h_counters;

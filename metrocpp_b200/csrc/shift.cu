@@ -149,7 +149,7 @@ int stage_shift(metro_ctx *ctx, const metro_params *prm)
 			if (N1 > 0) { fill_u8_kernel<<<GRID(N1), TPB, 0, st>>>(c1.type.as<u8>(), N1, 1); LAUNCHED(); }
 		}
 		n0 = c1;                                                 // the buffers move with the struct
-		n0.id_rank = DevBuf(); n0.id_rank_gen = 0; n0.id_rank_n = -1;
+		n0.id_rank_gen = 0; n0.id_rank_n = -1;                  // (the rank buffer moves along and is refilled: the token halos changed the order)
 		n0.n_halos = HH; n0.n_tuples = NN;
 	} else {
 		// catalogue 1 is borrowed device memory (metro_catalogue_adopt_device): the new catalogue 0 is built in fresh buffers
