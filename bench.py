@@ -725,7 +725,7 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
     one()                                                   # warm-up (allocations)
     ms, d2h, info = timed(steps, narrow)
     tt = eng.timings()                                      # device timings of the last match of the timed steps
-    match_dev = {"device_ms": tt["total"], "path": tt["path"], "catalogue0_partitioned_under_upload": bool(tt["resident"]),
+    match_dev = {"device_ms": tt["total"], "path": tt["path"], "catalogue0_partitioned_under_upload": bool(tt["resident"] & 1), "catalogue1_pass_a_under_upload": bool(tt["resident"] & 2),
                  "pass_abcd_ms": [round(x, 3) for x in tt["sort_pass_ms"][:4]], "select_ms": round(tt["select"], 3)}
     wide = None
     if narrow:                                              # the same with full 64-bit IDs over the bus, for reference
@@ -758,7 +758,7 @@ def measure_e2e(eng, prm, dev, dist, steps, ids_glob):
             if k > 0:
                 c_ms.append((time.perf_counter() - t0c) * 1e3)
                 tt = eng.timings()
-                c_dev.append(tt["total"]); c_res.append((tt["path"], tt["resident"], [round(x, 2) for x in tt["sort_pass_ms"][:4]], round(tt["select"], 2)))
+                c_dev.append(tt["total"]); c_res.append((tt["path"], tt["resident"] & 1, [round(x, 2) for x in tt["sort_pass_ms"][:4]], round(tt["select"], 2)))
                 c_h2d = (p32.numel() * 4 if narrow else pid.numel() * 8) + off.numel() * 8
         ids_step = sum(info_c["n_tuples"])
         chain = {"value": ids_step / (statistics.median(c_ms) * 1e-3), "unit": UNIT, "ms_per_step": statistics.median(c_ms),
@@ -854,7 +854,7 @@ def run_chain_workload(args):
             tm = eng.timings()
             eng.shift_halos_parts(prm)
             torch.cuda.synchronize(dev)
-            steps.append({"wall_ms": (time.perf_counter() - t0) * 1e3, "device_ms": tm["total"], "path": tm["path"], "resident": tm["resident"],
+            steps.append({"wall_ms": (time.perf_counter() - t0) * 1e3, "device_ms": tm["total"], "path": tm["path"], "resident": tm["resident"] & 1, "pass_a_under_upload": bool(tm["resident"] & 2),
                           "ids": int(sum(info["n_tuples"])), "trees": int(info["n_trees"]), "tokens": int(info["n_tokens"]), "launches": tm["total_launches"],
                           "passes_ms": [round(x, 3) for x in tm["sort_pass_ms"][:4]], "select_ms": round(tm["select"], 3),
                           "h2d_bytes": cats[k][1].numel() * cats[k][1].element_size() + cats[k][2].numel() * 8 + (cats[k][3] if w["multi"] else 0)})

@@ -108,8 +108,9 @@ typedef struct {
 	float sort_pass_ms[8];          /* LSD path: per onesweep pass; partition path: [0] = pass A (pack + partition), [1] = pass B (partition),
 	                                 * [2] = pass C (bucket join, hits out), [3] = pass D (hit count) */
 	int32_t path;                   /* 0 = LSD radix sort + run-length join, 1 = partition join, 2 = wide-key sort (IDs too wide for the packed key) */
-	int32_t resident;               /* partition join: 1 = the key buckets of catalogue 0 were still resident from the previous pair
-	                                 * of the chain (only catalogue 1 and the token tuples were partitioned) */
+	int32_t resident;               /* partition join, bit 0: the key buckets of catalogue 0 were resident - from the previous pair of the chain,
+	                                 * or built while catalogue 1 was being uploaded (only catalogue 1 and the token tuples were
+	                                 * partitioned); bit 1: catalogue 1 had been through pass A chunk by chunk under its own upload */
 	float exchange_sendrecv;        /* multi-GPU: the grouped ncclSend/ncclRecv all-to-all alone (payload over NVLink; includes waiting
 	                                 * for the slowest peer to arrive); `exchange` also covers routing counts and the scatter */
 } metro_timings;

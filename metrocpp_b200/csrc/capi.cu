@@ -87,6 +87,7 @@ int metro_ctx_create(int device, metro_ctx **out)
 	ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaStreamCreateWithFlags(&ctx->eager_stream, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags(&ctx->ev_eager, cudaEventDisableTiming) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags(&ctx->ev_eager0, cudaEventDisableTiming) == cudaSuccess;
 	for (int i = 0; ok && i < 5; i++) ok = cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming) == cudaSuccess;
 	for (int i = 0; ok && i < 16; i++) ok = cudaEventCreate(&ctx->ev[i]) == cudaSuccess;
 	for (int i = 0; ok && i < SORT_MAX_PASSES + 1; i++) ok = cudaEventCreate(&ctx->ev_pass[i]) == cudaSuccess;
@@ -140,6 +141,7 @@ void metro_ctx_destroy(metro_ctx *ctx)
 	if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
 	if (ctx->eager_stream) cudaStreamDestroy(ctx->eager_stream);
 	if (ctx->ev_eager) cudaEventDestroy(ctx->ev_eager);
+	if (ctx->ev_eager0) cudaEventDestroy(ctx->ev_eager0);
 	cudaStreamDestroy(ctx->own_stream);
 	delete ctx;
 }
@@ -289,6 +291,9 @@ static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, cons
 	u64 *cnt = ctx->counters.as<u64>() + 16;      // [16] max pid, [17] #invalid, [18] min pid
 	CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * sizeof(u64), st));
 	CUDA_TRY(ctx, cudaMemsetAsync(cnt + 2, 0xFF, sizeof(u64), st));
+	// catalogue 1 of a pair whose catalogue 0 is (being) partitioned: pass A of every chunk right behind its check
+	ctx->e1_on = false;
+	if (slot == 1 && (rc = partition_eager1_begin(ctx, prm, N, H))) return rc;
 	if (N > 0) {
 		if (halo_offset) {
 			if (halo_offset[0] != 0 || halo_offset[H] != N) { metro_set_error(ctx, "halo_offset must run from 0 to n_tuples"); return METRO_ERR_INVALID; }
@@ -318,14 +323,17 @@ static int upload_tuples(metro_ctx *ctx, int slot, const metro_params *prm, cons
 				(u64) n, (u32) H, (u32) prm->nptypes, cnt);
 			CUDA_TRY(ctx, cudaGetLastError());
 			if (pid32) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_up[3 + k], st));
+			if ((rc = partition_eager1_chunk(ctx, c.pid.as<u64>() + lo, c.halo.as<u32>() + lo, cat->type ? c.type.as<u8>() + lo : nullptr, n))) return rc;
 		}
 	}
 	c.n_tuples = N;
 	c.gen = ctx->next_gen++;
 	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 16, cnt, 3 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+	if ((rc = partition_eager1_flush(ctx))) return rc;
 	CUDA_TRY(ctx, cudaStreamSynchronize(st));
 	c.max_pid = ctx->h_counters[16];
 	c.min_pid = N > 0 ? ctx->h_counters[18] : 0;
+	partition_eager1_end(ctx, c, ctx->h_counters[17] == 0);
 	if (ctx->h_counters[17] != 0) {
 		metro_set_error(ctx, "catalogue has %llu tuples with a halo index >= n_halos or a type >= nptypes", (unsigned long long) ctx->h_counters[17]);
 		return METRO_ERR_INVALID;
@@ -486,7 +494,7 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 				}
 				CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
 				if ((rc = stage_partition_join(ctx, Lp, PP, halo_bits, attempt == 0, &R, &hits, &fell_back, &mask, finer > 0))) return rc;
-				if (!fell_back) { part = true; ctx->timings.path = 1; ctx->timings.resident = attempt == 0; sort_launches = 4; if (attempt >= 1) ctx->part_finer = finer; }
+				if (!fell_back) { part = true; ctx->timings.path = 1; ctx->timings.resident = attempt == 0 ? (ctx->last_a1 ? 3 : 1) : 0; sort_launches = 4; if (attempt >= 1) ctx->part_finer = finer; }
 				else if (attempt >= 1) {
 					if ((mask & ~6u) != 0 || finer >= 2) break;      // region / record overflows are not cured by finer buckets: LSD path
 					finer++;
@@ -495,7 +503,7 @@ int metro_match_pair(metro_ctx *ctx, const metro_params *prm, metro_result_info 
 			if (!part) ctx->pid_base = pid_base;
 		}
 		// the wide-key and LSD front ends overwrite keys_a / keys_b: whatever buckets were resident there are gone
-		if (wide || !part) { ctx->resident.cat0 = false; ctx->resident.cat1 = false; }
+		if (wide || !part) { ctx->resident.cat0 = false; ctx->resident.cat1 = false; ctx->resident.a1 = false; }
 		if (wide) {
 			CUDA_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
 			if ((rc = stage_wide_join(ctx, L, pid_bits, &R, &hits, &sort_launches))) return rc;

@@ -76,6 +76,8 @@ struct PartResident {
 	u64 pid_base = 0;
 	i64 nmax_cap = 0;           // tuples per catalogue the plan was sized for
 	i64 tail0 = 0;
+	bool a1 = false;            // the level-1 regions of half1 hold catalogue 1 (gen a1_gen), partitioned under its upload with P / L / pid_base
+	u64 a1_gen = 0;
 };
 
 struct metro_ctx {
@@ -84,8 +86,11 @@ struct metro_ctx {
 	cudaStream_t own_stream = nullptr;   // the context's private stream
 	cudaStream_t copy_stream = nullptr;  // host -> device copies of an upload (overlapped with the per-chunk checks on `stream`)
 	cudaStream_t eager_stream = nullptr; // passes A and B of catalogue 0 while catalogue 1 is being uploaded (stage_partition_eager)
-	cudaEvent_t ev_eager = nullptr;
+	cudaEvent_t ev_eager = nullptr, ev_eager0 = nullptr;
 	bool eager_pending = false;
+	bool last_a1 = false;                // the last partition join found catalogue 1 already through pass A
+	bool e1_on = false;                  // pass A of catalogue 1 under its upload (partition_eager1_*)
+	u32 *e1_g1 = nullptr, *e1_ovf = nullptr;
 	cudaEvent_t ev_up[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 	char err[1024] = {0};
 	int nptypes = 0;
@@ -132,6 +137,10 @@ int stage_pack_hist(metro_ctx *ctx, const KeyLayout &L, const SortPlan &plan);  
 bool partition_join_plan(const metro_ctx *ctx, const KeyLayout &L, i64 N, PartPlan *out, i64 *nmax_cap, int finer, i64 nmax_known = -1);     // partjoin.cu
 int stage_partition_eager(metro_ctx *ctx, const metro_params *prm);
 int partition_eager_join(metro_ctx *ctx);
+int partition_eager1_begin(metro_ctx *ctx, const metro_params *prm, i64 N, i64 H);
+int partition_eager1_chunk(metro_ctx *ctx, const u64 *pid, const u32 *halo, const u8 *type, i64 n);
+int partition_eager1_flush(metro_ctx *ctx);
+void partition_eager1_end(metro_ctx *ctx, const DevCatalogue &c, bool ok);
 int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, int rec_halo_bits, bool reuse0, i64 *n_records, i64 *n_hits, bool *fell_back,
 			 u32 *overflow_mask, bool finer_plan);
 int stage_prereduce(metro_ctx *ctx, const u64 *key, const u32 *cnt, i64 R, int halo_bits, int type_bits, bool swapped, i64 x_lo, i64 x_hi, DevBuf *W,

@@ -1213,7 +1213,8 @@ struct PartState {
 	uint4 *units;
 };
 
-static int part_state_reserve(metro_ctx *ctx, const PartPlan &P, int rec_halo_bits, int type_bits, PartState *S)
+// grow_ok = false: return 1 instead of (re)allocating a buffer that is too small (another stream may be using it)
+static int part_state_reserve(metro_ctx *ctx, const PartPlan &P, int rec_halo_bits, int type_bits, PartState *S, bool grow_ok = true)
 {
 	const DevCatalogue &c0 = ctx->cat[0];
 	S->nbk = 1ull << (P.b1 + P.b2);                                        // buckets per catalogue
@@ -1223,15 +1224,19 @@ static int part_state_reserve(metro_ctx *ctx, const PartPlan &P, int rec_halo_bi
 	// streams (resident part: hit_hist_kernel; the rest: pass A), each over-estimating by up to HIST_SAMPLE tiles
 	S->hits_cap = 2ull * ((u64) c0.n_tuples + 2ull * HIST_SAMPLE * PT_TILE) + (u64) (S->hp.slack + 2) * S->hp.nbh;
 	int rc;
-	// keys_a: level-1 regions, dead after pass B and reused for the hit regions
-	if ((rc = dev_reserve(ctx, ctx->keys_a, (std::max((size_t) S->nb1 * P.cap1, (size_t) S->hits_cap) + PT_TILE) * 8 + 64))) return rc;
-	if ((rc = dev_reserve(ctx, ctx->keys_b, ((size_t) S->nb * P.cap2 + PT_TILE) * 8 + 64))) return rc;
+	const size_t need_a = (std::max((size_t) S->nb1 * P.cap1, (size_t) S->hits_cap) + PT_TILE) * 8 + 64, need_b = ((size_t) S->nb * P.cap2 + PT_TILE) * 8 + 64;
 	// small state: [g1 nb1*CSTRIDE][hit_cnt 1024*CSTRIDE][t0 1024*CSTRIDE][g2 nb][hit_cap 1024][ovf, n_units, pad..16] u32, then hit_base u64[1024],
 	// units uint4[HR_MAX_UNITS]
 	const size_t n32 = (size_t) S->nb1 * CSTRIDE + 2 * (size_t) HIT_MAX_PARTS * CSTRIDE + S->nb + HIT_MAX_PARTS + 16;
 	const size_t off_base = (n32 * 4 + 15) & ~(size_t) 15;
 	const size_t off_units = off_base + (size_t) HIT_MAX_PARTS * 8;
-	if ((rc = dev_reserve(ctx, ctx->part_counts, off_units + (size_t) HR_MAX_UNITS * 16))) return rc;
+	const size_t need_c = off_units + (size_t) HR_MAX_UNITS * 16;
+	if (!grow_ok && (!ctx->keys_a.p || ctx->keys_a.cap < need_a || !ctx->keys_b.p || ctx->keys_b.cap < need_b || !ctx->part_counts.p || ctx->part_counts.cap < need_c))
+		return 1;
+	// keys_a: level-1 regions, dead after pass B and reused for the hit regions
+	if ((rc = dev_reserve(ctx, ctx->keys_a, need_a))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->keys_b, need_b))) return rc;
+	if ((rc = dev_reserve(ctx, ctx->part_counts, need_c))) return rc;
 	S->g1 = ctx->part_counts.as<u32>(); S->hit_cnt = S->g1 + S->nb1 * CSTRIDE; S->t0 = S->hit_cnt + (size_t) HIT_MAX_PARTS * CSTRIDE;
 	S->g2 = S->t0 + (size_t) HIT_MAX_PARTS * CSTRIDE; S->hit_cap = S->g2 + S->nb;
 	S->ovf = S->hit_cap + HIT_MAX_PARTS; S->n_units = S->ovf + 1;
@@ -1267,9 +1272,17 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	u64 *counters = ctx->counters.as<u64>();
 	PartResident &R = ctx->resident;
 	const int half0 = reuse0 ? R.half0 : 0, half1 = 1 - half0;          // halves of keys_b / g2 that hold catalogue 0 / 1
-	R.cat0 = false; R.cat1 = false;                                     // re-established at the end
-	// everything is cleared except (reuse0) the level-2 fill counters of the resident half
-	CUDA_TRY(ctx, cudaMemsetAsync(g1, 0, (size_t) (g2 - g1) * 4, st));
+	// catalogue 1 went through pass A chunk by chunk while it was uploaded (partition_eager1_*): its level-1 regions and their fill
+	// counters are in place
+	const bool a1 = reuse0 && R.a1 && R.a1_gen == c1.gen;
+	ctx->last_a1 = a1;
+	R.cat0 = false; R.cat1 = false; R.a1 = false;                       // re-established at the end
+	// everything is cleared except (reuse0) the level-2 fill counters of the resident half and (a1) the level-1 counters of catalogue 1
+	if (a1) {
+		const size_t hw = (size_t) (nb1 / 2) * CSTRIDE;                 // level-1 counter words of one catalogue
+		CUDA_TRY(ctx, cudaMemsetAsync(g1 + (size_t) half0 * hw, 0, hw * 4, st));
+		CUDA_TRY(ctx, cudaMemsetAsync(hit_cnt, 0, (size_t) (g2 - hit_cnt) * 4, st));
+	} else CUDA_TRY(ctx, cudaMemsetAsync(g1, 0, (size_t) (g2 - g1) * 4, st));
 	CUDA_TRY(ctx, cudaMemsetAsync(g2 + (size_t) half1 * nbk, 0, (size_t) nbk * 4, st));
 	if (!reuse0) CUDA_TRY(ctx, cudaMemsetAsync(g2 + (size_t) half0 * nbk, 0, (size_t) nbk * 4, st));
 	CUDA_TRY(ctx, cudaMemsetAsync(hit_cap, 0, (size_t) (HIT_MAX_PARTS + 16) * 4, st));
@@ -1285,7 +1298,7 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 			CUDA_TRY(ctx, cudaGetLastError());
 			ctx->launches++;
 		}
-		if (cnt <= 0) continue;
+		if (cnt <= 0 || (s == 1 && a1)) continue;
 		if ((rc = launch_part<true>(ctx, P.b1, (unsigned) div_up<i64>(cnt, PT_TILE), c.d_pid() + first, c.d_halo() + first, c.d_type() ? c.d_type() + first : nullptr,
 					    (u64) cnt, (u32) (s == 0 ? half0 : half1), L, P, ctx->keys_a.as<u64>(), nullptr, g1, ovf, s == 0 ? t0 : nullptr, hp))) return rc;
 	}
@@ -1374,7 +1387,7 @@ int stage_partition_eager(metro_ctx *ctx, const metro_params *prm)
 				(getenv("METRO_NO_RESIDENT") && atoi(getenv("METRO_NO_RESIDENT")));
 	PartResident &R = ctx->resident;
 	const DevCatalogue &c0 = ctx->cat[0];
-	R.cat0 = false; R.cat1 = false;
+	R.cat0 = false; R.cat1 = false; R.a1 = false;
 	if (off || !c0.valid || c0.n_tuples <= 0 || c0.n_halos <= 0 || !ctx->eager_stream) return METRO_OK;
 	u64 pid_base = c0.min_pid;
 	const int pid_bits = std::max(1, ceil_log2_u64(c0.max_pid - pid_base));
@@ -1400,10 +1413,13 @@ int stage_partition_eager(metro_ctx *ctx, const metro_params *prm)
 		cudaStream_t st = ctx->stream;
 		PartState S;
 		if ((rc = part_state_reserve(ctx, P, halo_bits, type_bits, &S))) break;
-		if (cudaMemsetAsync(S.g1, 0, (size_t) (S.hit_cap - S.g1) * 4 + (size_t) (HIT_MAX_PARTS + 16) * 4, st) != cudaSuccess) { rc = METRO_ERR_CUDA; break; }
+		if (cudaMemsetAsync(S.g1, 0, (size_t) (S.hit_cap - S.g1) * 4 + (size_t) (HIT_MAX_PARTS + 16) * 4, st) != cudaSuccess ||
+		    cudaEventRecord(ctx->ev_eager0, st) != cudaSuccess) { rc = METRO_ERR_CUDA; break; }         // (the upload of catalogue 1 adds to these counters)
 		if ((rc = launch_part<true>(ctx, P.b1, (unsigned) div_up<i64>(c0.n_tuples, PT_TILE), c0.d_pid(), c0.d_halo(), c0.d_type(), (u64) c0.n_tuples, 0u, L, P,
 					    ctx->keys_a.as<u64>(), nullptr, S.g1, S.ovf, nullptr, S.hp))) break;
-		if ((rc = launch_part<false>(ctx, P.b2, (unsigned) (S.nb1 * P.tiles1), ctx->keys_a.as<u64>(), nullptr, nullptr, 0, 0, L, P, ctx->keys_b.as<u64>(), S.g1, S.g2,
+		// pass B over the level-1 regions of catalogue 0 only (the first half): those of catalogue 1 may be filling up at this moment
+		// (partition_eager1_chunk on the compute stream)
+		if ((rc = launch_part<false>(ctx, P.b2, (unsigned) ((S.nb1 / 2) * P.tiles1), ctx->keys_a.as<u64>(), nullptr, nullptr, 0, 0, L, P, ctx->keys_b.as<u64>(), S.g1, S.g2,
 					     S.ovf, nullptr, S.hp))) break;
 		ctx->h_counters[61] = ~0ull;
 		if (cudaMemcpyAsync(ctx->h_counters + 61, S.ovf, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaEventRecord(ctx->ev_eager, st) != cudaSuccess) {
@@ -1428,4 +1444,74 @@ int partition_eager_join(metro_ctx *ctx)
 	CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_eager));
 	if ((u32) ctx->h_counters[61] != 0) ctx->resident.cat0 = false;
 	return METRO_OK;
+}
+
+
+// ---- pass A of catalogue 1 under its own upload -------------------------------------------------------------------------------
+// When the buckets of catalogue 0 are resident (chain step) or being built (stage_partition_eager), layout and plan of the coming
+// pair are fixed, so every chunk of catalogue 1 can go through pass A as soon as it has been checked - on the compute stream, while
+// the next chunk crosses the bus.  metro_match_pair then starts at pass B.  If the finished catalogue does not fit the plan after
+// all (ID range, size, an overflowed region), the marker is not set and the pair partitions it again.
+static bool eager_switched_off()
+{
+	static const bool off = (getenv("METRO_NO_EAGER") && atoi(getenv("METRO_NO_EAGER"))) || (getenv("METRO_FORCE_LSD") && atoi(getenv("METRO_FORCE_LSD"))) ||
+				(getenv("METRO_NO_RESIDENT") && atoi(getenv("METRO_NO_RESIDENT")));
+	return off;
+}
+
+int partition_eager1_begin(metro_ctx *ctx, const metro_params *prm, i64 N, i64 H)
+{
+	PartResident &R = ctx->resident;
+	const DevCatalogue &c0 = ctx->cat[0];
+	ctx->e1_on = false;
+	R.a1 = false;
+	if (eager_switched_off() || !R.cat0 || !c0.valid || R.gen != c0.gen || N <= 0 || H <= 0 || N > R.nmax_cap) return METRO_OK;
+	const int type_bits = prm->nptypes > 1 ? ceil_log2_u64((u64) prm->nptypes - 1) : 0;
+	if (type_bits != R.L.type_bits || std::max(1, ceil_log2_u64((u64) (H - 1))) > R.L.halo_bits) return METRO_OK;
+	PartState S;
+	// (while the eager partition of catalogue 0 is running nothing may be reallocated; it reserved the same sizes)
+	const int rc = part_state_reserve(ctx, R.P, R.L.halo_bits, type_bits, &S, !ctx->eager_pending);
+	if (rc > 0) return METRO_OK;
+	if (rc) return rc;
+	cudaStream_t st = ctx->stream;
+	if (ctx->eager_pending) CUDA_TRY(ctx, cudaStreamWaitEvent(st, ctx->ev_eager0, 0));      // its counters are cleared by then
+	const size_t hw = (size_t) (S.nb1 / 2) * CSTRIDE;
+	ctx->e1_g1 = S.g1;
+	ctx->e1_ovf = S.ovf + 2;                                                           // a flag of its own, next to the pair's
+	CUDA_TRY(ctx, cudaMemsetAsync(S.g1 + (size_t) R.half1 * hw, 0, hw * 4, st));
+	CUDA_TRY(ctx, cudaMemsetAsync(ctx->e1_ovf, 0, 4, st));
+	ctx->e1_on = true;
+	return METRO_OK;
+}
+
+int partition_eager1_chunk(metro_ctx *ctx, const u64 *pid, const u32 *halo, const u8 *type, i64 n)
+{
+	if (!ctx->e1_on || n <= 0) return METRO_OK;
+	const PartResident &R = ctx->resident;
+	const u64 keep_base = ctx->pid_base;
+	ctx->pid_base = R.pid_base;                                                       // (launch_part packs with ctx->pid_base)
+	HitPlan hp = {};
+	const int rc = launch_part<true>(ctx, R.P.b1, (unsigned) div_up<i64>(n, PT_TILE), pid, halo, type, (u64) n, (u32) R.half1, R.L, R.P, ctx->keys_a.as<u64>(), nullptr,
+					 ctx->e1_g1, ctx->e1_ovf, nullptr, hp);
+	ctx->pid_base = keep_base;
+	return rc;
+}
+
+// before the upload's final synchronisation: bring the overflow flag along
+int partition_eager1_flush(metro_ctx *ctx)
+{
+	if (!ctx->e1_on) return METRO_OK;
+	ctx->h_counters[63] = ~0ull;
+	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_counters + 63, ctx->e1_ovf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	return METRO_OK;
+}
+
+// after it: does the finished catalogue fit the plan it was partitioned with?
+void partition_eager1_end(metro_ctx *ctx, const DevCatalogue &c, bool ok)
+{
+	if (!ctx->e1_on) return;
+	ctx->e1_on = false;
+	PartResident &R = ctx->resident;
+	R.a1 = ok && (u32) ctx->h_counters[63] == 0 && c.n_tuples > 0 && c.min_pid >= R.pid_base && ceil_log2_u64(c.max_pid - R.pid_base) <= R.L.pid_bits;
+	R.a1_gen = c.gen;
 }

@@ -197,7 +197,7 @@ int stage_shift(metro_ctx *ctx, const metro_params *prm)
 	PartResident &R = ctx->resident;
 	if (R.cat1 && R.gen == c1.gen) { R.cat0 = true; R.gen = n0.gen; R.half0 = R.half1; R.half1 = 1 - R.half0; R.tail0 = N1; }
 	else R.cat0 = false;
-	R.cat1 = false;
+	R.cat1 = false; R.a1 = false;
 	if (move) {
 		// the buffers of the old catalogue 0 stay with slot 1 for the next upload (no free, no allocation in a chain step)
 		DevCatalogue keep;

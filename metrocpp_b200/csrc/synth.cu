@@ -182,7 +182,7 @@ extern "C" int metro_synth_pair_device(metro_ctx *ctx, const metro_params *prm, 
 	CUDA_TRY(ctx, cudaSetDevice(ctx->device));
 	int rc = partition_eager_join(ctx);
 	if (rc) return rc;
-	ctx->resident.cat0 = false; ctx->resident.cat1 = false;
+	ctx->resident.cat0 = false; ctx->resident.cat1 = false; ctx->resident.a1 = false;
 	HostTable HT;
 	rc = build_table(spec, prm->nptypes, HT, ctx->err, sizeof ctx->err);
 	if (rc) return rc;

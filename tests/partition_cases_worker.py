@@ -45,7 +45,7 @@ def run_case(eng, name, c0, c1, prm, expect_path=None, expect_resident=None):
     compare_result_with_oracle(res, binding.match_pair(oprm, to_oracle_catalogue(c0), to_oracle_catalogue(c1)))
     if expect_path is not None:
         assert path == expect_path, (name, path, expect_path)
-    if expect_resident is not None:
+    if expect_resident is not None:                # bit 0: catalogue 0's buckets resident; bit 1: catalogue 1 partitioned under its upload
         assert resident == expect_resident, (name, resident, expect_resident)
     print(f"CASE {name} path={path} eager={resident} hits={res.info['n_hits']} pairs={res.info['n_pairs']} ok", flush=True)
 
@@ -62,7 +62,7 @@ def main():
     earlier = [x[: int(0.9 * len(x))] for x in later]
     order = rng.permutation(len(earlier))
     run_case(eng, "plain", catalogue(later, 10**6, rng), catalogue([earlier[i] for i in order], 2 * 10**6, rng), prm, expect_path=1,
-             expect_resident=0 if os.environ.get("METRO_NO_EAGER") == "1" else 1)
+             expect_resident=0 if os.environ.get("METRO_NO_EAGER") == "1" else 3)
 
     # 1b. hashed 64-bit particle IDs (pid + snap + halo + type do not fit one 64-bit key): the wide-key front end; the
     #     trees must be those of the same pair with narrow IDs (only the equality of IDs matters)
@@ -145,7 +145,9 @@ def main():
         assert len(steps) == 5 and all(p == 1 for p, _, _ in steps), steps
         # resident from the second pair on (and, with the eager partition, in the first), unless the catalogue outgrows the plan (the
         # ZOOM flavour doubles the token tuples at every orphan step: src/MergerTree.cpp:597-603)
-        assert sum(r for _, r, _ in steps[1:]) >= (3 if flavour == "gather" else 1), steps
+        assert sum(r & 1 for _, r, _ in steps[1:]) >= (3 if flavour == "gather" else 1), steps
+        # whenever catalogue 0's buckets were resident, catalogue 1 had been through pass A under its upload (unless switched off)
+        assert all(r in ((0, 1) if os.environ.get("METRO_NO_EAGER") == "1" else (0, 3)) for _, r, _ in steps), steps
         assert sum(t for _, _, t in steps) > 0, steps                                  # token tuples were appended to resident buckets
         print(f"CASE resident_chain_{flavour} steps={steps} ok", flush=True)
 

@@ -29,7 +29,7 @@ def test_chain_workload_vs_oracle(name, n_snaps, halos, tuples, multi, flavour, 
 
     def on_step(e, res):
         t = e.timings()
-        seen["resident"] += t["resident"]; seen["partition"] += t["path"] == 1; seen["tokens"] += res.info["n_tokens"]
+        seen["resident"] += t["resident"] & 1; seen["partition"] += t["path"] == 1; seen["tokens"] += res.info["n_tokens"]
     out = engine_run_chain(eng, snaps, params, flavour, check_oracle=True, on_step=on_step)
     eng.close()
     assert len(out) == n_snaps - 1
