@@ -1377,18 +1377,23 @@ int stage_partition_join(metro_ctx *ctx, const KeyLayout &L, const PartPlan &P, 
 	return METRO_OK;
 }
 
+static bool eager_switched_off()
+{
+	static const bool off = (getenv("METRO_NO_EAGER") && atoi(getenv("METRO_NO_EAGER"))) || (getenv("METRO_FORCE_LSD") && atoi(getenv("METRO_FORCE_LSD"))) ||
+				(getenv("METRO_NO_RESIDENT") && atoi(getenv("METRO_NO_RESIDENT")));
+	return off;
+}
+
 // Eager partition of catalogue 0 (called at the end of its upload): passes A and B of its tuples run on the context's side stream
 // while the caller is still sending catalogue 1 over the bus; the pair then starts with catalogue 0's buckets resident, exactly like
 // the second pair of a chain.  Layout and plan are guessed from catalogue 0 alone (same ID range, at most 1/8 more tuples, at most
 // twice the halos in catalogue 1); if the pair does not fit them, metro_match_pair plans afresh and this work is lost, nothing else.
 int stage_partition_eager(metro_ctx *ctx, const metro_params *prm)
 {
-	static const bool off = (getenv("METRO_NO_EAGER") && atoi(getenv("METRO_NO_EAGER"))) || (getenv("METRO_FORCE_LSD") && atoi(getenv("METRO_FORCE_LSD"))) ||
-				(getenv("METRO_NO_RESIDENT") && atoi(getenv("METRO_NO_RESIDENT")));
 	PartResident &R = ctx->resident;
 	const DevCatalogue &c0 = ctx->cat[0];
 	R.cat0 = false; R.cat1 = false; R.a1 = false;
-	if (off || !c0.valid || c0.n_tuples <= 0 || c0.n_halos <= 0 || !ctx->eager_stream) return METRO_OK;
+	if (eager_switched_off() || !c0.valid || c0.n_tuples <= 0 || c0.n_halos <= 0 || !ctx->eager_stream) return METRO_OK;
 	u64 pid_base = c0.min_pid;
 	const int pid_bits = std::max(1, ceil_log2_u64(c0.max_pid - pid_base));
 	{	// the same preference as metro_match_pair: base 0, else a multiple of 2^pid_bits, when it costs no key bit
@@ -1452,13 +1457,6 @@ int partition_eager_join(metro_ctx *ctx)
 // pair are fixed, so every chunk of catalogue 1 can go through pass A as soon as it has been checked - on the compute stream, while
 // the next chunk crosses the bus.  metro_match_pair then starts at pass B.  If the finished catalogue does not fit the plan after
 // all (ID range, size, an overflowed region), the marker is not set and the pair partitions it again.
-static bool eager_switched_off()
-{
-	static const bool off = (getenv("METRO_NO_EAGER") && atoi(getenv("METRO_NO_EAGER"))) || (getenv("METRO_FORCE_LSD") && atoi(getenv("METRO_FORCE_LSD"))) ||
-				(getenv("METRO_NO_RESIDENT") && atoi(getenv("METRO_NO_RESIDENT")));
-	return off;
-}
-
 int partition_eager1_begin(metro_ctx *ctx, const metro_params *prm, i64 N, i64 H)
 {
 	PartResident &R = ctx->resident;
