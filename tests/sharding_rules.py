@@ -1,4 +1,5 @@
-"""Host-side rules of the multi-GPU layout (mirrors csrc/comm.cu; used by bench.py and the tests).
+"""Host-side rules of the multi-GPU layout: a numpy mirror of metrocpp_b200/csrc/comm.cu for tests/test_sharding_gloo.py (test
+infrastructure - the product routes on the device; tests/test_multi_gpu.py checks comm.cu itself against the oracle).
 
 * tuples of BOTH catalogues are sharded by particle-ID range, so a particle's memberships all
   live on one rank and sort + join need no communication;

@@ -9,7 +9,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import metrocpp_b200 as mb
-from metrocpp_b200 import sharding
+from tests import sharding_rules as sharding
 
 
 def pair_counts(c0, c1):
