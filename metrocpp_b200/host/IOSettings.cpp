@@ -206,35 +206,73 @@ static inline const char *ScanU64(const char *p, const char *end, uint64_t &v)
 	return p;
 }
 
+// The lines of an _halos file that start in [p, stop): every line is parsed on its own from its first character (a '#' in column 0
+// is a comment, src/IOSettings.cpp:753), so chunks of whole lines can be parsed side by side.  `end` = end of the NUL-terminated buffer.
+static void ParseHaloLines(const char *p, const char *stop, const char *end, int nPTypes, std::vector<Halo> &out)
+{
+	while (p < stop) {
+		const char *q = SkipSpace(p, end);
+		if (q >= end) break;
+		if (*p == '#' || *q == '\n') { p = NextLine(p, end); continue; }
+		Halo h;
+		char *e;
+		h.ID = strtoull(q, &e, 10);
+		(void) strtol(e, &e, 10);                                  // hostHalo: read into a dummy by the reference
+		h.nSub = (int) strtol(e, &e, 10);
+		h.mTot = strtof(e, &e);
+		long npart = strtol(e, &e, 10);
+		for (int i = 0; i < 3; i++) h.X[i] = strtof(e, &e);
+		for (int i = 0; i < 3; i++) h.V[i] = strtof(e, &e);
+		// ReadLineAHF (src/IOSettings.cpp:961-989): all particles are booked under type 1
+		h.nPart[0] = 0;
+		if (nPTypes > 1) h.nPart[1] = (int) npart; else h.nPart[0] = (int) npart;
+		out.push_back(h);
+		p = NextLine(p, end);
+	}
+}
+
 void IOSettings::ReadHalos()
 {
 	std::vector<Halo> &out = locHalos[iUseCat];
 	out.clear();
+	unsigned nThreads = std::thread::hardware_concurrency();
+	const char *forced = getenv("METRO_INGEST_THREADS");               // tests: force the chunked path on small files
+	if (forced && atoi(forced) > 0) nThreads = (unsigned) atoi(forced);
+	if (nThreads == 0) nThreads = 1;
+	if (nThreads > 64) nThreads = 64;
+	auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 	for (const std::string &path : haloFiles[iNumCat]) {
 		std::string buf;
+		const double t0 = now();
 		if (!ReadWholeFile(path, buf)) Fatal("file " + path + " not found");
-		const char *p = buf.data(), *end = p + buf.size();
+		const double t1 = now();
+		const char *base = buf.data(), *end = base + buf.size();
 		size_t before = out.size();
-		while (p < end) {
-			const char *q = SkipSpace(p, end);
-			if (q >= end) break;
-			if (*p == '#' || *q == '\n') { p = NextLine(p, end); continue; }        // '#' in column 0 (src/IOSettings.cpp:753)
-			Halo h;
-			char *e;
-			h.ID = strtoull(q, &e, 10);
-			(void) strtol(e, &e, 10);                                  // hostHalo: read into a dummy by the reference
-			h.nSub = (int) strtol(e, &e, 10);
-			h.mTot = strtof(e, &e);
-			long npart = strtol(e, &e, 10);
-			for (int i = 0; i < 3; i++) h.X[i] = strtof(e, &e);
-			for (int i = 0; i < 3; i++) h.V[i] = strtof(e, &e);
-			// ReadLineAHF (src/IOSettings.cpp:961-989): all particles are booked under type 1
-			h.nPart[0] = 0;
-			if (nPTypes > 1) h.nPart[1] = (int) npart; else h.nPart[0] = (int) npart;
-			out.push_back(h);
-			p = NextLine(p, end);
+		// chunks of whole lines, one per thread (10^6 halos are 100-400 MB of text: a second of strtof on one core)
+		const unsigned nt = (buf.size() < (1u << 20) && !forced) ? 1u : nThreads;
+		std::vector<const char *> cut(nt + 1, end);
+		cut[0] = base;
+		for (unsigned t = 1; t < nt; t++) {
+			const char *c = base + buf.size() / nt * t;
+			cut[t] = c <= cut[t - 1] ? cut[t - 1] : NextLine(c, end);
+		}
+		double t2 = t1;
+		if (nt == 1) ParseHaloLines(base, end, end, nPTypes, out);
+		else {
+			std::vector<std::vector<Halo>> part(nt);
+			std::vector<std::thread> th;
+			for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t] { ParseHaloLines(cut[t], cut[t + 1], end, nPTypes, part[t]); });
+			for (auto &x : th) x.join();
+			t2 = now();
+			size_t total = out.size();
+			for (auto &v : part) total += v.size();
+			out.reserve(total);
+			for (auto &v : part) out.insert(out.end(), v.begin(), v.end());
 		}
 		if (locTask == 0) printf("Reading %zu halos from file: %s\n", out.size() - before, path.c_str());
+		if (getenv("METRO_DEBUG"))
+			fprintf(stderr, "[metro] _halos ingest: %.1f MB, %zu halos, %u threads: read %.3f s, parse %.3f s, merge %.3f s\n", buf.size() / 1e6, out.size() - before, nt,
+				t1 - t0, (nt == 1 ? now() : t2) - t1, nt == 1 ? 0.0 : now() - t2);
 	}
 	nLocHalos[iUseCat] = (int) out.size();
 	slotDirty[iUseCat] = true;
@@ -243,8 +281,9 @@ void IOSettings::ReadHalos()
 // One text line of an _particles file, tokenised: first and second unsigned number (kNone = absent).
 static const uint64_t kNone = ~0ull;
 
-// Parses [p, end) (whole lines) into a[]/b[]: one entry per line, blank lines included.
-static void TokeniseLines(const char *p, const char *end, uint64_t *a, uint64_t *b)
+// Parses [p, end) (whole lines) into a[]/b[]: one entry per line, blank lines included.  Plain version: every access is bounds-checked
+// (the last 64 bytes of a chunk, and anything the fast loop below hands back).
+static size_t TokeniseTail(const char *p, const char *end, uint64_t *a, uint64_t *b)
 {
 	size_t k = 0;
 	while (p < end) {
@@ -258,6 +297,65 @@ static void TokeniseLines(const char *p, const char *end, uint64_t *a, uint64_t 
 		a[k] = x; b[k] = y; k++;
 		p = NextLine(q, end);
 	}
+	return k;
+}
+
+// Eight characters at a time: how many of the first bytes of w are decimal digits, and the value of eight digits (first character in
+// the lowest byte; zero bytes count as the digit 0).  Same value modulo 2^64 as the digit-by-digit loop of ScanU64.
+static inline uint64_t Load8(const char *p) { uint64_t w; memcpy(&w, p, 8); return w; }
+static inline unsigned DigitRun(uint64_t w)
+{
+	const uint64_t d = w - 0x3030303030303030ull;
+	const uint64_t nd = ((w + 0x4646464646464646ull) | d) & 0x8080808080808080ull;      // high bit set in every byte outside '0'..'9'
+	return nd ? (unsigned) (__builtin_ctzll(nd) >> 3) : 8u;
+}
+static inline uint64_t Parse8(uint64_t w)
+{
+	w = (w & 0x0F0F0F0F0F0F0F0Full) * 2561 >> 8;
+	w = (w & 0x00FF00FF00FF00FFull) * 6553601 >> 16;
+	return (w & 0x0000FFFF0000FFFFull) * 42949672960001ull >> 32;
+}
+static inline const char *ScanU64Fast(const char *p, const char *safe, uint64_t &v)      // 8 readable bytes behind every p < safe
+{
+	static const uint64_t pow10[8] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull};
+	uint64_t x = 0;
+	while (p < safe) {
+		const uint64_t w = Load8(p);
+		const unsigned n = DigitRun(w);
+		if (n == 8) { x = x * 100000000ull + Parse8(w); p += 8; continue; }
+		if (n) { x = x * pow10[n] + Parse8(w << ((8 - n) * 8)); p += n; }
+		break;
+	}
+	v = x;
+	return p;
+}
+
+// The same, without bounds checks while more than 64 bytes remain (172 MB, one thread: 0.53 -> 0.32 s).  A line that does not end
+// inside that range is handed to the plain version from its first character.
+static void TokeniseLines(const char *p, const char *end, uint64_t *a, uint64_t *b)
+{
+	size_t k = 0;
+	const char *safe = end - p > 64 ? end - 64 : p;
+	while (p < safe) {
+		const char *q = p;
+		while (q < safe && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
+		if (q >= safe) break;
+		uint64_t x = kNone, y = kNone;
+		if ((unsigned) (*q - '0') <= 9u) {
+			q = ScanU64Fast(q, safe, x);
+			while (q < safe && (*q == ' ' || *q == '\t' || *q == '\r')) q++;
+			if (q >= safe) break;
+			if ((unsigned) (*q - '0') <= 9u) q = ScanU64Fast(q, safe, y);
+			if (q >= safe) break;
+		}
+		if (*q != '\n') {
+			q = (const char *) memchr(q, '\n', (size_t) (safe - q));
+			if (!q) break;
+		}
+		a[k] = x; b[k] = y; k++;
+		p = q + 1;
+	}
+	TokeniseTail(p, end, a + k, b + k);
 }
 
 static size_t CountLines(const char *p, const char *end)
@@ -322,10 +420,19 @@ void IOSettings::ReadParticles()
 		}
 		for (unsigned t = 0; t < nt; t++) lineOff[t + 1] += lineOff[t];
 		const size_t nLines = lineOff[nt];
-		std::unique_ptr<uint64_t[]> A(new uint64_t[nLines + 1]), B(new uint64_t[nLines + 1]);     // uninitialised: every entry is written below
+		// token arrays: uninitialised (every entry is written below) and kept for the next file / snapshot - a fresh 16 bytes per line
+		// would be page-faulted in again every time (a quarter of the tokenising time)
+		static std::unique_ptr<uint64_t[]> tokA, tokB;
+		static size_t tokCap = 0;
+		if (nLines + 1 > tokCap) {
+			tokA.reset(); tokB.reset();
+			tokCap = nLines + 1 + nLines / 8;
+			tokA.reset(new uint64_t[tokCap]); tokB.reset(new uint64_t[tokCap]);
+		}
+		uint64_t *const A = tokA.get(), *const B = tokB.get();
 		{
 			std::vector<std::thread> th;
-			for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t] { TokeniseLines(cut[t], cut[t + 1], A.get() + lineOff[t], B.get() + lineOff[t]); });
+			for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t] { TokeniseLines(cut[t], cut[t + 1], A + lineOff[t], B + lineOff[t]); });
 			for (auto &x : th) x.join();
 		}
 		double t2 = now();

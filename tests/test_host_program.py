@@ -134,6 +134,52 @@ def test_ingest_grammar_edge_cases(tmp_path):
         assert "2 particle lines belong to halo IDs that are not in the halo catalogue" in err
 
 
+def test_ingest_fast_tokeniser_lexical_corners(tmp_path):
+    """The eight-digits-at-a-time tokeniser of the _particles reader against a plain Python parse of the same text: 1-19 digit IDs
+    (8-, 9-, 16- and 17-digit ones included), leading / trailing blanks and tabs, CRLF line ends, extra tokens behind the type, a
+    last line without a newline; whole file in one chunk and cut into 3 / 8 / 61 chunks (every chunk ends in a bounds-checked
+    tail of 64 bytes, so the cuts move the hand-over between the two code paths across all of these line shapes)."""
+    import random
+    rnd = random.Random(20261020)
+    inp = tmp_path / "input"
+    inp.mkdir(); (tmp_path / "output").mkdir()
+    n_halos = 300
+    sizes = [rnd.randint(0, 120) for _ in range(n_halos)]
+    digits = [1, 2, 7, 8, 9, 10, 15, 16, 17, 18, 19]
+    lines, exp = [f"{n_halos}"], []
+    for h, n in enumerate(sizes):
+        lines.append(f"{n} {1000 + h}" + rnd.choice(["", " ", "\r", "  \t"]))
+        for _ in range(n):
+            nd = rnd.choice(digits)
+            pid = rnd.randint(10 ** (nd - 1) if nd > 1 else 0, min(10 ** nd - 1, 2 ** 63 - 1))
+            ty = rnd.choice([0, 1, 4, 5])
+            lead = rnd.choice(["", "", "", " ", "\t ", "   "])
+            mid = rnd.choice([" ", " ", "\t", "    "])
+            tail = rnd.choice(["", "", "", " ", "\r", " \r", " 77 extra", "\tx"])
+            lines.append(f"{lead}{pid}{mid}{ty}{tail}")
+            exp.append((pid, h, ty))
+    text = "\n".join(lines)                                   # no newline behind the last line
+    for number, z in ((10, "0.000"), (9, "0.100")):
+        with open(inp / f"snapshot_{number:03d}.z{z}.AHF_halos", "w") as f:
+            f.write("#ID(1) hostHalo(2) numSubStruct(3) Mvir(4) npart(5) Xc Yc Zc VXc VYc VZc\n")
+            for h, n in enumerate(sizes):
+                f.write(f"{1000 + h} 0 0 1.0e10 {n} 1 2 3 4 5 6\n")
+        with open(inp / f"snapshot_{number:03d}.z{z}.AHF_particles", "w", newline="") as f:
+            f.write(text)
+    cfg = tmp_path / "config.cfg"
+    cfg.write_text("inputFormat = AHF\nhaloSuffix = AHF_halos\npartSuffix = AHF_particles\nhaloPrefix = snapshot_\npartPrefix = snapshot_\n"
+                   f"cpuString = .\nsplitString = _\npathMetroCpp = {tmp_path}/\npathInput = {inp}/\nboxSize = 1000.0\nnChunks = 1\nnSnapsUse = 2\n"
+                   f"nGrid = 4\npathOutput = {tmp_path}/output/\noutPrefix = t_\noutSuffix = mtree\nminPartHalo = 1\nminPartCmp = 1\nfacOrphanSteps = 15\n"
+                   "cosmologicalModel = Planck\nnTreeChunks = 1\ntreeFlavour = zoom\nnPTypes = 6\nnoPType = 0\n")
+    exp_ck = fnv(p + 0x9E3779B97F4A7C15 * (h + 1) + t for p, h, t in exp)
+    assert len(text) > 100_000
+    for threads in (1, 3, 8, 61):
+        parsed, _ = _parse_only(str(cfg), threads)
+        assert len(parsed) == 2
+        for kv in parsed:
+            assert int(kv["halos"]) == n_halos and int(kv["tuples"]) == len(exp) and int(kv["tuple_ck"]) == exp_ck, (threads, kv)
+
+
 # ---- .mtree reader compatibility (SURVEY 8f-4) ---------------------------------------------------------------------------------
 def reader_rules(text):
     """What the reference's own post-processing reader makes of a .mtree file (python/mtreelib/read_mtree.py:98-145): a line of 4
