@@ -206,6 +206,18 @@ static inline const char *ScanU64(const char *p, const char *end, uint64_t &v)
 	return p;
 }
 
+static size_t CountLines(const char *p, const char *end)
+{
+	size_t n = 0;
+	while (p < end) {
+		const char *nl = (const char *) memchr(p, '\n', (size_t) (end - p));
+		n++;
+		if (!nl) break;
+		p = nl + 1;
+	}
+	return n;
+}
+
 // The lines of an _halos file that start in [p, stop): every line is parsed on its own from its first character (a '#' in column 0
 // is a comment, src/IOSettings.cpp:753), so chunks of whole lines can be parsed side by side.  `end` = end of the NUL-terminated buffer.
 static void ParseHaloLines(const char *p, const char *stop, const char *end, int nPTypes, std::vector<Halo> &out)
@@ -261,7 +273,11 @@ void IOSettings::ReadHalos()
 		else {
 			std::vector<std::vector<Halo>> part(nt);
 			std::vector<std::thread> th;
-			for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t] { ParseHaloLines(cut[t], cut[t + 1], end, nPTypes, part[t]); });
+			for (unsigned t = 0; t < nt; t++)
+				th.emplace_back([&, t] {
+					part[t].reserve(CountLines(cut[t], cut[t + 1]));        // no regrowth while parsing
+					ParseHaloLines(cut[t], cut[t + 1], end, nPTypes, part[t]);
+				});
 			for (auto &x : th) x.join();
 			t2 = now();
 			size_t total = out.size();
@@ -356,18 +372,6 @@ static void TokeniseLines(const char *p, const char *end, uint64_t *a, uint64_t 
 		p = q + 1;
 	}
 	TokeniseTail(p, end, a + k, b + k);
-}
-
-static size_t CountLines(const char *p, const char *end)
-{
-	size_t n = 0;
-	while (p < end) {
-		const char *nl = (const char *) memchr(p, '\n', (size_t) (end - p));
-		n++;
-		if (!nl) break;
-		p = nl + 1;
-	}
-	return n;
 }
 
 // AHF _particles reader (reference src/IOSettings.cpp:599-689: "nHalos", then per halo "nPart haloID" and
